@@ -1,0 +1,124 @@
+"""ctypes binding of libmtlora_b200.so — the C ABI declared in include/mtlora_b200.h.
+
+This is the only place the shared library is opened. There is no CPU or PyTorch fallback: when the library is
+missing or a call fails, a RuntimeError carrying mtl_last_error() is raised.
+"""
+import ctypes
+import os
+
+MTL_MAX_TASKS = 7
+MTL_ABI_VERSION = 1
+MTL_MODE_MATRIX = 0
+MTL_ACT_NONE, MTL_ACT_GELU = 0, 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmtlora_b200.so")
+
+c_void_p, c_int, c_int32, c_int64, c_float, c_uint64 = (
+    ctypes.c_void_p, ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_uint64)
+
+
+class LinearCfg(ctypes.Structure):
+    """mtl_linear_cfg (include/mtlora_b200.h) == constructor arguments of MTLoRALinear, models/lora.py:161-176."""
+    _fields_ = [
+        ("M", c_int64),
+        ("in_features", c_int32),
+        ("out_features", c_int32),
+        ("n_tasks", c_int32),
+        ("x_tasks_given", c_int32),
+        ("shared_mode", c_int32),
+        ("r_shared", c_int32),
+        ("r_task", c_int32 * MTL_MAX_TASKS),
+        ("scale_shared", c_float),
+        ("scale_task", c_float * MTL_MAX_TASKS),
+        ("dropout_p", c_float),
+        ("dropout_seed", c_uint64),
+        ("rows_per_sample", c_int32),
+    ]
+
+
+_CFG_P = ctypes.POINTER(LinearCfg)
+_PP = ctypes.POINTER(c_void_p)
+
+# name -> (restype, argtypes); must list every function include/mtlora_b200.h declares (tests check this).
+SIGNATURES = {
+    "mtl_abi_version": (c_int, []),
+    "mtl_last_error": (ctypes.c_char_p, []),
+    "mtl_linear_rank_pad": (c_int, [_CFG_P]),
+    "mtl_linear_rank_offset": (c_int, [_CFG_P, c_int]),
+    "mtl_linear_pack": (c_int, [_CFG_P, c_void_p, c_void_p, _PP, _PP, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mtl_cast_transpose": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "mtl_linear_fwd": (c_int, [_CFG_P, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
+                               c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "mtl_linear_bwd_input": (c_int, [_CFG_P, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p]),
+    "mtl_linear_bwd_params": (c_int, [_CFG_P, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p]),
+    "mtl_xty": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_int32, c_float,
+                        c_void_p]),
+    "mtl_window_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
+                                         c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_float,
+                                         c_uint64, c_void_p]),
+    "mtl_window_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
+                                         c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float,
+                                         c_void_p]),
+    "mtl_roll_and_window_partition_forward": (c_int, [c_void_p, c_void_p] + [c_int32] * 7 + [c_void_p]),
+    "mtl_roll_and_window_partition_backward": (c_int, [c_void_p, c_void_p] + [c_int32] * 7 + [c_void_p]),
+    "mtl_window_merge_and_roll_forward": (c_int, [c_void_p, c_void_p] + [c_int32] * 7 + [c_void_p]),
+    "mtl_window_merge_and_roll_backward": (c_int, [c_void_p, c_void_p] + [c_int32] * 7 + [c_void_p]),
+    "mtl_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                  c_int64, c_int32, c_float, c_int32, c_int32, c_int32, c_float, c_uint64, c_void_p]),
+    "mtl_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "mtl_dropout": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_uint64, c_void_p]),
+    "mtl_scale_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int32, c_void_p]),
+    "mtl_add": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "mtl_sum_streams": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p]),
+}
+
+_lib = None
+launch_count = 0  # number of C-ABI compute calls issued by this process (bench.py reports kernel launches from it)
+
+
+def load():
+    """Open the library (once) and declare every signature. Raises if the extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the sm_100a extension is not built. Run `make` at the repo root or "
+            "`python -c 'import __graft_entry__ as g; g.build()'`. There is no CPU/PyTorch fallback for this path.")
+    import torch  # noqa: F401  (loads the CUDA runtime the library links against)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here == header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.mtl_abi_version()
+    if got != MTL_ABI_VERSION:
+        raise RuntimeError(f"libmtlora_b200.so ABI version {got} != expected {MTL_ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Invoke a C-ABI function returning an int status; raise RuntimeError(mtl_last_error()) on failure."""
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.mtl_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{name} failed (code {rc}): {msg}")
+    launch_count += 1
+    return rc
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,504 @@
+// Fused shifted-window attention for sm_100a.
+//
+// Replaces, in one kernel per direction (reference models/swin_transformer_mtlora.py):
+//   torch.roll + window_partition      :338-342   (or kernels/window_process WindowProcess)
+//   q*scale, q@k^T, + relative-position bias gather, + attn_mask, softmax, attn@v   :194-220
+//   window_reverse + torch.roll back   :365-377   (or WindowProcessReverse)
+// The cyclic shift / partition / reverse are pure index math on the gather of q,k,v rows and on the
+// scatter of the output rows, so activations stay in (B, H, W, C) token order end to end.
+//
+// A window is N = ws*ws <= 64 tokens with head_dim 32: one CTA (4 warps x 16 query rows) handles a
+// (window, head) pair per iteration on mma.sync m16n8k16 tiles. Arithmetic intensity is ~24 FLOP/B,
+// so the kernel is bound by the HBM gather/scatter, not the tensor pipe.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace mtl {
+
+namespace {
+
+constexpr int HD = 32;        // head dim (fixed in Swin: C / num_heads == 32)
+constexpr int NP = 64;        // padded tokens per window
+constexpr int QS = 40;        // smem row stride (bf16) for [NP][HD] tiles: 80 B, conflict-free ldmatrix
+constexpr int PS = 72;        // smem row stride (bf16) for [NP][NP] tiles
+
+struct WinGeom {
+  int H, W, ws, shift, nwh, nww, N;
+};
+
+// token index (within window) -> row in the (B*H*W) token matrix, with the cyclic shift folded in
+__device__ __forceinline__ int token_row(const WinGeom& g, int b, int wy, int wx, int i) {
+  const int iy = i / g.ws, ix = i - iy * g.ws;
+  int r = wy * g.ws + iy + g.shift;
+  int c = wx * g.ws + ix + g.shift;
+  if (r >= g.H) r -= g.H;
+  if (c >= g.W) c -= g.W;
+  return (b * g.H + r) * g.W + c;
+}
+// region id used by the analytic SW-MSA mask (:297-319), on rolled coordinates
+__device__ __forceinline__ int region_id(const WinGeom& g, int wy, int wx, int i) {
+  const int iy = i / g.ws, ix = i - iy * g.ws;
+  const int r = wy * g.ws + iy, c = wx * g.ws + ix;
+  const int rr = r < g.H - g.ws ? 0 : (r < g.H - g.shift ? 1 : 2);
+  const int rc = c < g.W - g.ws ? 0 : (c < g.W - g.shift ? 1 : 2);
+  return rr * 3 + rc;
+}
+
+// S (16 x 64 per warp, c-layout) = scale * Q K^T + bias + mask ; padded key columns -> -inf
+__device__ __forceinline__ void scores_16x64(float (&s)[8][4], const __nv_bfloat16* Qs, const __nv_bfloat16* Ks,
+                                             int warp, int lane) {
+  uint32_t aq[2][4];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+    ldmatrix_x4(aq[ks], smem_u32(Qs + (warp * 16 + (lane & 15)) * QS + ks * 16 + (lane >> 4) * 8));
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    uint32_t bk[4];
+    ldmatrix_x4(bk, smem_u32(Ks + (nt * 8 + (lane & 7)) * QS + (lane >> 3) * 8));
+    s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    const uint32_t b0[2] = {bk[0], bk[1]}, b1[2] = {bk[2], bk[3]};
+    mma_bf16_16816(s[nt], aq[0], b0);
+    mma_bf16_16816(s[nt], aq[1], b1);
+  }
+}
+
+struct AttnParams {
+  const __nv_bfloat16* qkv;   // [B*H*W, 3C]
+  const float* rpb;           // [(2ws-1)^2, nH]
+  const float* mask;          // optional explicit mask [nW_mask, N, N] (else analytic when shift > 0)
+  int n_mask;
+  __nv_bfloat16* out;         // [B*H*W, C]
+  __nv_bfloat16* out_drop;    // optional dropped copy (LoRA dropout for proj), same shape
+  float* lse;                 // [B*nW, nH, NP]
+  uint64_t drop_seed;
+  float drop_p;
+  int B, C, nH;
+  float scale;
+  WinGeom g;
+};
+
+__global__ void __launch_bounds__(128) win_attn_fwd_kernel(const AttnParams p) {
+  __shared__ __align__(16) __nv_bfloat16 Qs[NP * QS];
+  __shared__ __align__(16) __nv_bfloat16 Ks[NP * QS];
+  __shared__ __align__(16) __nv_bfloat16 Vs[NP * QS];
+  __shared__ float bias_s[225];
+  __shared__ int rows_s[NP];
+  __shared__ int reg_s[NP];
+
+  const int head = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g4 = lane >> 2, t4 = lane & 3;
+  const WinGeom g = p.g;
+  const int nW = g.nwh * g.nww;
+  const int n_win = p.B * nW;
+  const int tbl = (2 * g.ws - 1) * (2 * g.ws - 1);
+  for (int i = threadIdx.x; i < tbl; i += blockDim.x) bias_s[i] = p.rpb[i * p.nH + head];
+  const int C3 = 3 * p.C;
+
+  for (int win = blockIdx.x; win < n_win; win += gridDim.x) {
+    const int b = win / nW, wi = win - b * nW;
+    const int wy = wi / g.nww, wx = wi - wy * g.nww;
+    __syncthreads();  // previous iteration done with smem
+    if (threadIdx.x < NP) {
+      const int i = threadIdx.x;
+      rows_s[i] = i < g.N ? token_row(g, b, wy, wx, i) : -1;
+      reg_s[i] = (i < g.N && g.shift > 0) ? region_id(g, wy, wx, i) : 0;
+    }
+    __syncthreads();
+    // gather q,k,v rows of this head: 3 tiles x 64 rows x 4 chunks of 16 B
+    for (int idx = threadIdx.x; idx < 3 * NP * 4; idx += blockDim.x) {
+      const int which = idx / (NP * 4), rem = idx - which * NP * 4;
+      const int i = rem >> 2, ch = rem & 3;
+      __nv_bfloat16* dst = (which == 0 ? Qs : which == 1 ? Ks : Vs) + i * QS + ch * 8;
+      const int row = rows_s[i];
+      const __nv_bfloat16* src = p.qkv + static_cast<size_t>(row < 0 ? 0 : row) * C3 + which * p.C + head * HD + ch * 8;
+      cp_async_16_zfill(smem_u32(dst), src, row >= 0);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+
+    float s[8][4];
+    scores_16x64(s, Qs, Ks, warp, lane);
+
+    // bias + mask + softmax on rows (warp*16 + g4) and (+8)
+    const int i0 = warp * 16 + g4, i1 = i0 + 8;
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = (e < 2) ? i0 : i1;
+        const int j = nt * 8 + t4 * 2 + (e & 1);
+        float v = -INFINITY;
+        if (j < g.N) {
+          const int ic = i < g.N ? i : 0;
+          const int iy = ic / g.ws, ix = ic - iy * g.ws, jy = j / g.ws, jx = j - jy * g.ws;
+          v = s[nt][e] * p.scale + bias_s[(iy - jy + g.ws - 1) * (2 * g.ws - 1) + (ix - jx + g.ws - 1)];
+          if (p.mask != nullptr) {
+            if (i < g.N) v += p.mask[(static_cast<size_t>(win % p.n_mask) * g.N + i) * g.N + j];
+          } else if (g.shift > 0 && reg_s[ic] != reg_s[j]) {
+            v += -100.0f;
+          }
+        }
+        s[nt][e] = v;
+        if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float m = (e < 2) ? mx0 : mx1;
+        const float pv = __expf(s[nt][e] - m);
+        s[nt][e] = pv;
+        if (e < 2) sum0 += pv; else sum1 += pv;
+      }
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+    if (p.lse != nullptr && t4 == 0) {
+      float* l = p.lse + (static_cast<size_t>(win) * p.nH + head) * NP;
+      l[i0] = mx0 + __logf(sum0);
+      l[i1] = mx1 + __logf(sum1);
+    }
+
+    // O = P V  (P from registers, V via transposed ldmatrix)
+    float o[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t ap[4];
+      ap[0] = pack_bf16x2(s[2 * kk][0] * inv0, s[2 * kk][1] * inv0);
+      ap[1] = pack_bf16x2(s[2 * kk][2] * inv1, s[2 * kk][3] * inv1);
+      ap[2] = pack_bf16x2(s[2 * kk + 1][0] * inv0, s[2 * kk + 1][1] * inv0);
+      ap[3] = pack_bf16x2(s[2 * kk + 1][2] * inv1, s[2 * kk + 1][3] * inv1);
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t bv[4];
+        ldmatrix_x4_trans(bv, smem_u32(Vs + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * QS + np * 16 + (lane >> 4) * 8));
+        const uint32_t b0[2] = {bv[0], bv[1]}, b1[2] = {bv[2], bv[3]};
+        mma_bf16_16816(o[np * 2], ap, b0);
+        mma_bf16_16816(o[np * 2 + 1], ap, b1);
+      }
+    }
+    __syncthreads();  // everyone done reading Qs -> reuse as output staging
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      *reinterpret_cast<uint32_t*>(Qs + i0 * QS + nt * 8 + t4 * 2) = pack_bf16x2(o[nt][0], o[nt][1]);
+      *reinterpret_cast<uint32_t*>(Qs + i1 * QS + nt * 8 + t4 * 2) = pack_bf16x2(o[nt][2], o[nt][3]);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < NP * 4; idx += blockDim.x) {
+      const int i = idx >> 2, ch = idx & 3;
+      const int row = rows_s[i];
+      if (row < 0) continue;
+      const uint4 v = *reinterpret_cast<const uint4*>(Qs + i * QS + ch * 8);
+      const size_t off = static_cast<size_t>(row) * p.C + head * HD + ch * 8;
+      *reinterpret_cast<uint4*>(p.out + off) = v;
+      if (p.out_drop != nullptr) {
+        const float keep_scale = 1.f / (1.f - p.drop_p);
+        const uint32_t thr = dropout_threshold(p.drop_p);
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float lo = dropout_hash(p.drop_seed, off + 2 * e) >= thr ? bf16lo_to_f32(w4[e]) * keep_scale : 0.f;
+          const float hi = dropout_hash(p.drop_seed, off + 2 * e + 1) >= thr ? bf16hi_to_f32(w4[e]) * keep_scale : 0.f;
+          o4[e] = pack_bf16x2(lo, hi);
+        }
+        *reinterpret_cast<uint4*>(p.out_drop + off) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+      }
+    }
+  }
+}
+
+struct AttnBwdParams {
+  const __nv_bfloat16* qkv;   // [B*H*W, 3C]
+  const __nv_bfloat16* dout;  // [B*H*W, C]
+  const float* rpb;
+  const float* mask;
+  int n_mask;
+  const float* lse;           // [B*nW, nH, NP]
+  __nv_bfloat16* dqkv;        // [B*H*W, 3C]
+  float* drpb;                // [(2ws-1)^2, nH] accumulated with atomics (caller zero-fills), or null
+  int B, C, nH;
+  float scale;
+  WinGeom g;
+};
+
+__global__ void __launch_bounds__(128) win_attn_bwd_kernel(const AttnBwdParams p) {
+  __shared__ __align__(16) __nv_bfloat16 Qs[NP * QS];
+  __shared__ __align__(16) __nv_bfloat16 Ks[NP * QS];
+  __shared__ __align__(16) __nv_bfloat16 Vs[NP * QS];
+  __shared__ __align__(16) __nv_bfloat16 dOs[NP * QS];
+  __shared__ __align__(16) __nv_bfloat16 Ps[NP * PS];
+  __shared__ __align__(16) __nv_bfloat16 dSs[NP * PS];
+  __shared__ float bias_s[225];
+  __shared__ float dbias_s[225];
+  __shared__ int rows_s[NP];
+  __shared__ int reg_s[NP];
+
+  const int head = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g4 = lane >> 2, t4 = lane & 3;
+  const WinGeom g = p.g;
+  const int nW = g.nwh * g.nww;
+  const int n_win = p.B * nW;
+  const int tbl = (2 * g.ws - 1) * (2 * g.ws - 1);
+  for (int i = threadIdx.x; i < tbl; i += blockDim.x) {
+    bias_s[i] = p.rpb[i * p.nH + head];
+    dbias_s[i] = 0.f;
+  }
+  const int C3 = 3 * p.C;
+  float dsacc[8][4];  // sum over this CTA's windows of dS (for d relative_position_bias_table)
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) dsacc[nt][0] = dsacc[nt][1] = dsacc[nt][2] = dsacc[nt][3] = 0.f;
+
+  for (int win = blockIdx.x; win < n_win; win += gridDim.x) {
+    const int b = win / nW, wi = win - b * nW;
+    const int wy = wi / g.nww, wx = wi - wy * g.nww;
+    __syncthreads();
+    if (threadIdx.x < NP) {
+      const int i = threadIdx.x;
+      rows_s[i] = i < g.N ? token_row(g, b, wy, wx, i) : -1;
+      reg_s[i] = (i < g.N && g.shift > 0) ? region_id(g, wy, wx, i) : 0;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 4 * NP * 4; idx += blockDim.x) {
+      const int which = idx / (NP * 4), rem = idx - which * NP * 4;
+      const int i = rem >> 2, ch = rem & 3;
+      const int row = rows_s[i];
+      const size_t r = static_cast<size_t>(row < 0 ? 0 : row);
+      __nv_bfloat16* dst;
+      const __nv_bfloat16* src;
+      if (which < 3) {
+        dst = (which == 0 ? Qs : which == 1 ? Ks : Vs) + i * QS + ch * 8;
+        src = p.qkv + r * C3 + which * p.C + head * HD + ch * 8;
+      } else {
+        dst = dOs + i * QS + ch * 8;
+        src = p.dout + r * p.C + head * HD + ch * 8;
+      }
+      cp_async_16_zfill(smem_u32(dst), src, row >= 0);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // ---- recompute P = exp(S - lse) --------------------------------------------------------
+    float s[8][4];
+    scores_16x64(s, Qs, Ks, warp, lane);
+    const int i0 = warp * 16 + g4, i1 = i0 + 8;
+    const float* l = p.lse + (static_cast<size_t>(win) * p.nH + head) * NP;
+    const float lse0 = l[i0], lse1 = l[i1];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = (e < 2) ? i0 : i1;
+        const int j = nt * 8 + t4 * 2 + (e & 1);
+        float pv = 0.f;
+        if (j < g.N && i < g.N) {
+          const int iy = i / g.ws, ix = i - iy * g.ws, jy = j / g.ws, jx = j - jy * g.ws;
+          float v = s[nt][e] * p.scale + bias_s[(iy - jy + g.ws - 1) * (2 * g.ws - 1) + (ix - jx + g.ws - 1)];
+          if (p.mask != nullptr) v += p.mask[(static_cast<size_t>(win % p.n_mask) * g.N + i) * g.N + j];
+          else if (g.shift > 0 && reg_s[i] != reg_s[j]) v += -100.0f;
+          pv = __expf(v - ((e < 2) ? lse0 : lse1));
+        }
+        s[nt][e] = pv;
+      }
+    }
+    // ---- dP = dO V^T -------------------------------------------------------------------------
+    float dp[8][4];
+    scores_16x64(dp, dOs, Vs, warp, lane);
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      d0 += s[nt][0] * dp[nt][0] + s[nt][1] * dp[nt][1];
+      d1 += s[nt][2] * dp[nt][2] + s[nt][3] * dp[nt][3];
+    }
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+    // dS = P * (dP - delta); stash P and dS (bf16) for the transposed products
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      float ds[4];
+      ds[0] = s[nt][0] * (dp[nt][0] - d0);
+      ds[1] = s[nt][1] * (dp[nt][1] - d0);
+      ds[2] = s[nt][2] * (dp[nt][2] - d1);
+      ds[3] = s[nt][3] * (dp[nt][3] - d1);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dsacc[nt][e] += ds[e];
+      const int col = nt * 8 + t4 * 2;
+      *reinterpret_cast<uint32_t*>(Ps + i0 * PS + col) = pack_bf16x2(s[nt][0], s[nt][1]);
+      *reinterpret_cast<uint32_t*>(Ps + i1 * PS + col) = pack_bf16x2(s[nt][2], s[nt][3]);
+      *reinterpret_cast<uint32_t*>(dSs + i0 * PS + col) = pack_bf16x2(ds[0], ds[1]);
+      *reinterpret_cast<uint32_t*>(dSs + i1 * PS + col) = pack_bf16x2(ds[2], ds[3]);
+      dp[nt][0] = ds[0]; dp[nt][1] = ds[1]; dp[nt][2] = ds[2]; dp[nt][3] = ds[3];
+    }
+    // ---- dQ = scale * dS K  (A from registers, K via transposed ldmatrix) --------------------
+    float dq[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) dq[nt][0] = dq[nt][1] = dq[nt][2] = dq[nt][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t a[4];
+      a[0] = pack_bf16x2(dp[2 * kk][0], dp[2 * kk][1]);
+      a[1] = pack_bf16x2(dp[2 * kk][2], dp[2 * kk][3]);
+      a[2] = pack_bf16x2(dp[2 * kk + 1][0], dp[2 * kk + 1][1]);
+      a[3] = pack_bf16x2(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t bk[4];
+        ldmatrix_x4_trans(bk, smem_u32(Ks + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * QS + np * 16 + (lane >> 4) * 8));
+        const uint32_t b0[2] = {bk[0], bk[1]}, b1[2] = {bk[2], bk[3]};
+        mma_bf16_16816(dq[np * 2], a, b0);
+        mma_bf16_16816(dq[np * 2 + 1], a, b1);
+      }
+    }
+    __syncthreads();  // Ps / dSs complete; all warps finished reading Ks,Vs for S, dP, dQ
+    // ---- dK = scale * dS^T Q ; dV = P^T dO  (this warp owns key rows warp*16 .. +15) ----------
+    float dk[4][4], dv[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      dk[nt][0] = dk[nt][1] = dk[nt][2] = dk[nt][3] = 0.f;
+      dv[nt][0] = dv[nt][1] = dv[nt][2] = dv[nt][3] = 0.f;
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {  // reduction over query rows i in steps of 16
+      uint32_t ads[4], apt[4];
+      const int mi = lane >> 3;
+      const int krow = kk * 16 + (lane & 7) + (mi >> 1) * 8;
+      const int mcol = warp * 16 + (mi & 1) * 8;
+      ldmatrix_x4_trans(ads, smem_u32(dSs + krow * PS + mcol));
+      ldmatrix_x4_trans(apt, smem_u32(Ps + krow * PS + mcol));
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t bq[4], bo[4];
+        const int brow = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int bcol = np * 16 + (lane >> 4) * 8;
+        ldmatrix_x4_trans(bq, smem_u32(Qs + brow * QS + bcol));
+        ldmatrix_x4_trans(bo, smem_u32(dOs + brow * QS + bcol));
+        const uint32_t q0[2] = {bq[0], bq[1]}, q1[2] = {bq[2], bq[3]};
+        const uint32_t o0[2] = {bo[0], bo[1]}, o1[2] = {bo[2], bo[3]};
+        mma_bf16_16816(dk[np * 2], ads, q0);
+        mma_bf16_16816(dk[np * 2 + 1], ads, q1);
+        mma_bf16_16816(dv[np * 2], apt, o0);
+        mma_bf16_16816(dv[np * 2 + 1], apt, o1);
+      }
+    }
+    __syncthreads();  // all reads of Qs/Ks/Vs/dOs done -> reuse Qs,Ks,Vs as dq,dk,dv staging
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int col = nt * 8 + t4 * 2;
+      *reinterpret_cast<uint32_t*>(Qs + i0 * QS + col) = pack_bf16x2(dq[nt][0] * p.scale, dq[nt][1] * p.scale);
+      *reinterpret_cast<uint32_t*>(Qs + i1 * QS + col) = pack_bf16x2(dq[nt][2] * p.scale, dq[nt][3] * p.scale);
+      *reinterpret_cast<uint32_t*>(Ks + i0 * QS + col) = pack_bf16x2(dk[nt][0] * p.scale, dk[nt][1] * p.scale);
+      *reinterpret_cast<uint32_t*>(Ks + i1 * QS + col) = pack_bf16x2(dk[nt][2] * p.scale, dk[nt][3] * p.scale);
+      *reinterpret_cast<uint32_t*>(Vs + i0 * QS + col) = pack_bf16x2(dv[nt][0], dv[nt][1]);
+      *reinterpret_cast<uint32_t*>(Vs + i1 * QS + col) = pack_bf16x2(dv[nt][2], dv[nt][3]);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 3 * NP * 4; idx += blockDim.x) {
+      const int which = idx / (NP * 4), rem = idx - which * NP * 4;
+      const int i = rem >> 2, ch = rem & 3;
+      const int row = rows_s[i];
+      if (row < 0) continue;
+      const __nv_bfloat16* src = (which == 0 ? Qs : which == 1 ? Ks : Vs) + i * QS + ch * 8;
+      *reinterpret_cast<uint4*>(p.dqkv + static_cast<size_t>(row) * C3 + which * p.C + head * HD + ch * 8) =
+          *reinterpret_cast<const uint4*>(src);
+    }
+  }
+
+  if (p.drpb != nullptr) {
+    __syncthreads();
+    const int i0 = warp * 16 + g4, i1 = i0 + 8;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = (e < 2) ? i0 : i1;
+        const int j = nt * 8 + t4 * 2 + (e & 1);
+        if (i < g.N && j < g.N) {
+          const int iy = i / g.ws, ix = i - iy * g.ws, jy = j / g.ws, jx = j - jy * g.ws;
+          atomicAdd(&dbias_s[(iy - jy + g.ws - 1) * (2 * g.ws - 1) + (ix - jx + g.ws - 1)], dsacc[nt][e]);
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < tbl; i += blockDim.x) atomicAdd(p.drpb + i * p.nH + head, dbias_s[i]);
+  }
+}
+
+int check_geom(int B, int H, int W, int C, int nH, int ws, int shift) {
+  MTL_REQUIRE(B > 0 && H > 0 && W > 0, "attention: empty input");
+  MTL_REQUIRE(C == nH * HD, "attention: head_dim must be 32 (C=%d, heads=%d)", C, nH);
+  MTL_REQUIRE(ws >= 1 && ws <= 8, "attention: window size %d unsupported (1..8)", ws);
+  MTL_REQUIRE(H % ws == 0 && W % ws == 0, "attention: H,W (%d,%d) not divisible by window %d", H, W, ws);
+  MTL_REQUIRE(shift >= 0 && shift < ws, "attention: shift_size must be in [0, window)");
+  return 0;
+}
+
+}  // namespace
+
+int launch_win_attn_fwd(const void* qkv, const float* rpb, const float* mask, int n_mask, void* out, void* out_drop,
+                        float* lse, int B, int H, int W, int C, int nH, int ws, int shift, float scale,
+                        float drop_p, uint64_t drop_seed, cudaStream_t stream) {
+  if (int e = check_geom(B, H, W, C, nH, ws, shift)) return e;
+  AttnParams p;
+  p.qkv = static_cast<const __nv_bfloat16*>(qkv);
+  p.rpb = rpb;
+  p.mask = mask;
+  p.n_mask = n_mask > 0 ? n_mask : 1;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.out_drop = static_cast<__nv_bfloat16*>(out_drop);
+  p.lse = lse;
+  p.drop_seed = drop_seed;
+  p.drop_p = drop_p;
+  p.B = B; p.C = C; p.nH = nH; p.scale = scale;
+  p.g = WinGeom{H, W, ws, shift, H / ws, W / ws, ws * ws};
+  const int n_win = B * p.g.nwh * p.g.nww;
+  int gx = n_win;
+  const int cap = (148 * 8 + nH - 1) / nH;  // ~8 CTAs per SM in flight across heads
+  if (gx > cap) gx = cap;
+  win_attn_fwd_kernel<<<dim3(gx, nH), 128, 0, stream>>>(p);
+  MTL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_win_attn_bwd(const void* qkv, const void* dout, const float* rpb, const float* mask, int n_mask,
+                        const float* lse, void* dqkv, float* drpb, int B, int H, int W, int C, int nH, int ws,
+                        int shift, float scale, cudaStream_t stream) {
+  if (int e = check_geom(B, H, W, C, nH, ws, shift)) return e;
+  AttnBwdParams p;
+  p.qkv = static_cast<const __nv_bfloat16*>(qkv);
+  p.dout = static_cast<const __nv_bfloat16*>(dout);
+  p.rpb = rpb;
+  p.mask = mask;
+  p.n_mask = n_mask > 0 ? n_mask : 1;
+  p.lse = lse;
+  p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  p.drpb = drpb;
+  p.B = B; p.C = C; p.nH = nH; p.scale = scale;
+  p.g = WinGeom{H, W, ws, shift, H / ws, W / ws, ws * ws};
+  const int n_win = B * p.g.nwh * p.g.nww;
+  int gx = n_win;
+  const int cap = (148 * 4 + nH - 1) / nH;
+  if (gx > cap) gx = cap;
+  win_attn_bwd_kernel<<<dim3(gx, nH), 128, 0, stream>>>(p);
+  MTL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace mtl

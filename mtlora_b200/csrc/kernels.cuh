@@ -1,0 +1,54 @@
+// Internal launcher declarations (C++ linkage) shared by the C ABI layer in api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mtl {
+
+// attention.cu ------------------------------------------------------------------------------------
+int launch_win_attn_fwd(const void* qkv, const float* rpb, const float* mask, int n_mask, void* out, void* out_drop,
+                        float* lse, int B, int H, int W, int C, int nH, int ws, int shift, float scale,
+                        float drop_p, uint64_t drop_seed, cudaStream_t stream);
+int launch_win_attn_bwd(const void* qkv, const void* dout, const float* rpb, const float* mask, int n_mask,
+                        const float* lse, void* dqkv, float* drpb, int B, int H, int W, int C, int nH, int ws,
+                        int shift, float scale, cudaStream_t stream);
+
+// rowwise.cu --------------------------------------------------------------------------------------
+// LayerNorm over the last dim of [rows, C] (bf16 in/out, fp32 statistics and affine parameters).
+// merge != 0: input is a (B, H, W, C/4) token grid and each output row is the PatchMerging 2x2 gather
+// (reference swin_transformer_mtlora.py:462-466) of 4 source rows, so C = 4 * C_src.
+int launch_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, void* y_drop, long drop_rows,
+                         float* mean, float* rstd, long rows, int C, float eps, int merge, int H, int W, float drop_p,
+                         uint64_t drop_seed, cudaStream_t stream);
+// dx (= LN backward, optionally + dres) ; dgamma/dbeta accumulated with atomics into fp32 buffers.
+int launch_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                         const void* dres, void* dx, float* dgamma, float* dbeta, long rows, int C, int merge,
+                         int H, int W, cudaStream_t stream);
+// kernels/window_process equivalents (bitwise gathers), elem_size in {2, 4}
+int launch_roll_partition(const void* in, void* out, int B, int H, int W, int C, int shift, int ws, int elem_size,
+                          int inverse, cudaStream_t stream);
+int launch_merge_roll(const void* in, void* out, int B, int H, int W, int C, int shift, int ws, int elem_size,
+                      int inverse, cudaStream_t stream);
+// y = x * mask / (1-p) with the counter-based mask shared by every kernel (index = flat element index)
+int launch_dropout(const void* x, void* y, long n, float p, uint64_t seed, cudaStream_t stream);
+// y[s, m, :] = x[s, m, :] * scale[s, m / rows_per_sample]   (DropPath gradient pre-scale)
+int launch_scale_rows(const void* x, const float* scale, void* y, int S, long M, int C, int rows_per_sample,
+                      cudaStream_t stream);
+// out[i] = sum_{s<S} x[s, i] (+ extra[i] when extra != null), bf16 in/out, fp32 accumulation
+int launch_sum_streams(const void* x, const void* extra, void* out, int S, long n, cudaStream_t stream);
+// out = a + b (bf16)
+int launch_add(const void* a, const void* b, void* out, long n, cudaStream_t stream);
+// pack fp32 adapter parameters into the bf16 operand layouts of the fused linear kernel
+int launch_pack_adapters(const float* const* a_ptrs, const float* const* b_ptrs, const int* ranks, const int* offs,
+                         int n_adapt, int K, int N, int R_pad, void* a_cat, void* b_cat, void* a_cat_t, void* b_cat_t,
+                         cudaStream_t stream);
+// fp32 [rows, cols] -> bf16 copy and/or bf16 transposed copy
+int launch_cast_transpose(const float* w, void* w_bf16, void* wt_bf16, int rows, int cols, cudaStream_t stream);
+
+// xty.cu ------------------------------------------------------------------------------------------
+// C[a, b] += sum_m rowscale(m) * P[m, a] * Q[m, b]   (fp32 atomics; P, Q bf16 row-major with leading dims)
+// q_gelu != 0 applies exact GELU to Q elements on load (recomputing the fc2 input from the saved fc1 output).
+int launch_xty(const void* P, long ldp, const void* Q, long ldq, float* C, long ldc, long M, int a, int b,
+               const float* rowscale, int rows_per_sample, int q_gelu, float alpha, cudaStream_t stream);
+
+}  // namespace mtl

@@ -1,0 +1,546 @@
+// Row-wise / gather kernels of the Swin block: LayerNorm (optionally fused with the PatchMerging 2x2
+// gather), the roll+window-partition gathers of kernels/window_process, dropout, DropPath row scaling and
+// operand packing. All are HBM-bound streaming kernels: 16-byte vector accesses, one warp per row.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace mtl {
+
+namespace {
+
+// Source row pointer for output row `r`, segment `seg` (PatchMerging: 4 segments of Cs channels, order
+// (dy,dx) = (0,0),(1,0),(0,1),(1,1) as in swin_transformer_mtlora.py:462-466).
+__device__ __forceinline__ long merge_src_row(long r, int seg, int H, int W) {
+  const int H2 = H >> 1, W2 = W >> 1;
+  const long b = r / (static_cast<long>(H2) * W2);
+  const int rem = static_cast<int>(r - b * H2 * W2);
+  const int i = rem / W2, j = rem - i * W2;
+  return (b * H + 2 * i + (seg & 1)) * W + 2 * j + (seg >> 1);
+}
+
+struct LnFwdParams {
+  const __nv_bfloat16* x;
+  const float* gamma;
+  const float* beta;
+  __nv_bfloat16* y;
+  __nv_bfloat16* y_drop;
+  float* mean;
+  float* rstd;
+  long rows;
+  long drop_rows;  // only rows < drop_rows get a dropped copy (stream 0 of a stream-stacked input)
+  int C, merge, H, W;
+  float eps, drop_p;
+  uint64_t drop_seed;
+};
+
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const LnFwdParams p) {
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const int nvec = p.C >> 3;
+  const int Cs = p.merge ? p.C >> 2 : p.C;
+  const int vec_per_seg = Cs >> 3;
+  auto src_vec = [&](int v) -> const uint4* {
+    if (!p.merge) return reinterpret_cast<const uint4*>(p.x + row * p.C) + v;
+    const int seg = v / vec_per_seg;
+    return reinterpret_cast<const uint4*>(p.x + merge_src_row(row, seg, p.H, p.W) * Cs) + (v - seg * vec_per_seg);
+  };
+  float sum = 0.f, sq = 0.f;
+  for (int v = lane; v < nvec; v += 32) {
+    const uint4 q = __ldg(src_vec(v));
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = bf16lo_to_f32(w[e]), b = bf16hi_to_f32(w[e]);
+      sum += a + b;
+      sq += a * a + b * b;
+    }
+  }
+  sum = warp_sum(sum);
+  sq = warp_sum(sq);
+  const float mean = sum / p.C;
+  const float var = fmaxf(sq / p.C - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + p.eps);
+  if (lane == 0) {
+    if (p.mean) p.mean[row] = mean;
+    if (p.rstd) p.rstd[row] = rstd;
+  }
+  const uint32_t thr = dropout_threshold(p.drop_p);
+  const bool do_drop = p.y_drop != nullptr && row < p.drop_rows;
+  const float keep_scale = do_drop ? 1.f / (1.f - p.drop_p) : 1.f;
+  for (int v = lane; v < nvec; v += 32) {
+    const uint4 q = __ldg(src_vec(v));
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * v);
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * v + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta) + 2 * v);
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.beta) + 2 * v + 1);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      o[2 * e] = (bf16lo_to_f32(w[e]) - mean) * rstd * gg[2 * e] + bb[2 * e];
+      o[2 * e + 1] = (bf16hi_to_f32(w[e]) - mean) * rstd * gg[2 * e + 1] + bb[2 * e + 1];
+    }
+    const size_t off = static_cast<size_t>(row) * p.C + v * 8;
+    *reinterpret_cast<uint4*>(p.y + off) =
+        make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    if (do_drop) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        // the dropped copy is derived from the bf16-rounded value so that it equals D(y) exactly
+        const float r = __bfloat162float(__float2bfloat16_rn(o[e]));
+        o[e] = dropout_hash(p.drop_seed, off + e) >= thr ? r * keep_scale : 0.f;
+      }
+      *reinterpret_cast<uint4*>(p.y_drop + off) =
+          make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    }
+  }
+}
+
+struct LnBwdParams {
+  const __nv_bfloat16* dy;
+  const __nv_bfloat16* x;
+  const float* gamma;
+  const float* mean;
+  const float* rstd;
+  const __nv_bfloat16* dres;
+  __nv_bfloat16* dx;
+  float* dgamma;
+  float* dbeta;
+  long rows;
+  int C, merge, H, W;
+  int rows_per_cta;
+};
+
+// One warp per row. dgamma/dbeta: each lane owns the columns of vectors lane, lane+32, ... and keeps their
+// partial sums in registers across all rows of the CTA strip (C <= 1024); wider rows (PatchMerging LN(4C) of the
+// deep, short stages) fall back to shared-memory atomics. Per-CTA sums are flushed to the fp32 global
+// accumulators with one atomicAdd per column per CTA.
+template <bool REGS>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdParams p) {
+  extern __shared__ float red[];  // [2][C]
+  float* dg_s = red;
+  float* db_s = red + p.C;
+  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int nvec = p.C >> 3;
+  const int Cs = p.merge ? p.C >> 2 : p.C;
+  const int vec_per_seg = Cs >> 3;
+  const long row_begin = static_cast<long>(blockIdx.x) * p.rows_per_cta;
+  long row_end = row_begin + p.rows_per_cta;
+  if (row_end > p.rows) row_end = p.rows;
+  constexpr int VPL = REGS ? 4 : 1;
+  float dg_r[VPL][8], db_r[VPL][8];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dg_r[k][e] = db_r[k][e] = 0.f;
+
+  for (long row = row_begin + warp; row < row_end; row += nwarp) {
+    auto src_off = [&](int v) -> size_t {
+      if (!p.merge) return static_cast<size_t>(row) * p.C + v * 8;
+      const int seg = v / vec_per_seg;
+      return static_cast<size_t>(merge_src_row(row, seg, p.H, p.W)) * Cs + (v - seg * vec_per_seg) * 8;
+    };
+    const float mean = p.mean[row], rstd = p.rstd[row];
+    float s1 = 0.f, s2 = 0.f;  // sum(g), sum(g * xhat), g = dy * gamma
+    auto pass1 = [&](int v, int k) {
+      const uint4 qx = __ldg(reinterpret_cast<const uint4*>(p.x + src_off(v)));
+      const uint4 qd = __ldg(reinterpret_cast<const uint4*>(p.dy + static_cast<size_t>(row) * p.C + v * 8));
+      const uint32_t wx[4] = {qx.x, qx.y, qx.z, qx.w}, wd[4] = {qd.x, qd.y, qd.z, qd.w};
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * v);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * v + 1);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xv = (e & 1) ? bf16hi_to_f32(wx[e >> 1]) : bf16lo_to_f32(wx[e >> 1]);
+        const float dv = (e & 1) ? bf16hi_to_f32(wd[e >> 1]) : bf16lo_to_f32(wd[e >> 1]);
+        const float xh = (xv - mean) * rstd;
+        const float g = dv * gg[e];
+        s1 += g;
+        s2 += g * xh;
+        if (REGS) {
+          dg_r[k][e] += dv * xh;
+          db_r[k][e] += dv;
+        } else {
+          atomicAdd(&dg_s[v * 8 + e], dv * xh);
+          atomicAdd(&db_s[v * 8 + e], dv);
+        }
+      }
+    };
+    if (REGS) {
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int v = lane + 32 * k;
+        if (v < nvec) pass1(v, k);
+      }
+    } else {
+      for (int v = lane; v < nvec; v += 32) pass1(v, 0);
+    }
+    s1 = warp_sum(s1) / p.C;
+    s2 = warp_sum(s2) / p.C;
+    for (int v = lane; v < nvec; v += 32) {
+      const size_t so = src_off(v);
+      const uint4 qx = __ldg(reinterpret_cast<const uint4*>(p.x + so));
+      const uint4 qd = __ldg(reinterpret_cast<const uint4*>(p.dy + static_cast<size_t>(row) * p.C + v * 8));
+      const uint32_t wx[4] = {qx.x, qx.y, qx.z, qx.w}, wd[4] = {qd.x, qd.y, qd.z, qd.w};
+      uint32_t wr[4] = {0, 0, 0, 0};
+      if (p.dres) {
+        const uint4 qr = __ldg(reinterpret_cast<const uint4*>(p.dres + so));
+        wr[0] = qr.x; wr[1] = qr.y; wr[2] = qr.z; wr[3] = qr.w;
+      }
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * v);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * v + 1);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xv = (e & 1) ? bf16hi_to_f32(wx[e >> 1]) : bf16lo_to_f32(wx[e >> 1]);
+        const float dv = (e & 1) ? bf16hi_to_f32(wd[e >> 1]) : bf16lo_to_f32(wd[e >> 1]);
+        const float rv = (e & 1) ? bf16hi_to_f32(wr[e >> 1]) : bf16lo_to_f32(wr[e >> 1]);
+        const float xh = (xv - mean) * rstd;
+        o[e] = rstd * (dv * gg[e] - s1 - xh * s2) + rv;
+      }
+      *reinterpret_cast<uint4*>(p.dx + so) =
+          make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    }
+  }
+  if (REGS) {
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int v = lane + 32 * k;
+      if (v < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          atomicAdd(&dg_s[v * 8 + e], dg_r[k][e]);
+          atomicAdd(&db_s[v * 8 + e], db_r[k][e]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (p.dgamma) {
+    for (int i = threadIdx.x; i < p.C; i += blockDim.x) {
+      atomicAdd(p.dgamma + i, dg_s[i]);
+      atomicAdd(p.dbeta + i, db_s[i]);
+    }
+  }
+}
+
+// ---- kernels/window_process equivalents ----------------------------------------------------------
+// partition: out[b*nWin + wy*nW + wx, iy, ix, :] = in[b, (wy*ws+iy+shift) % H, (wx*ws+ix+shift) % W, :]
+// (torch.roll(x, (-shift,-shift)) + window_partition). `scatter` swaps source and destination, which is both
+// the backward of partition and the forward of window_reverse + roll(+shift).
+template <typename V>
+__global__ void window_gather_kernel(const V* __restrict__ in, V* __restrict__ out, int B, int H, int W, int CV,
+                                     int shift, int ws, int scatter) {
+  const long total = static_cast<long>(B) * H * W * CV;
+  const int nww = W / ws, nwh = H / ws;
+  for (long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % CV);
+    long t = idx / CV;  // window-ordered token index
+    const int ix = static_cast<int>(t % ws); t /= ws;
+    const int iy = static_cast<int>(t % ws); t /= ws;
+    const int wx = static_cast<int>(t % nww); t /= nww;
+    const int wy = static_cast<int>(t % nwh); t /= nwh;
+    const long b = t;
+    int r = wy * ws + iy + shift, q = wx * ws + ix + shift;
+    r %= H; if (r < 0) r += H;
+    q %= W; if (q < 0) q += W;
+    const long img = ((b * H + r) * W + q) * CV + c;
+    if (scatter) out[img] = in[idx];
+    else out[idx] = in[img];
+  }
+}
+
+__global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long n8, float p,
+                               uint64_t seed) {
+  const uint32_t thr = dropout_threshold(p);
+  const float ks = 1.f / (1.f - p);
+  for (long v = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; v < n8;
+       v += static_cast<long>(gridDim.x) * blockDim.x) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(x) + v);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float lo = dropout_hash(seed, v * 8 + 2 * e) >= thr ? bf16lo_to_f32(w[e]) * ks : 0.f;
+      const float hi = dropout_hash(seed, v * 8 + 2 * e + 1) >= thr ? bf16hi_to_f32(w[e]) * ks : 0.f;
+      o[e] = pack_bf16x2(lo, hi);
+    }
+    reinterpret_cast<uint4*>(y)[v] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void scale_rows_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
+                                  __nv_bfloat16* __restrict__ y, int S, long M, int CV, int rows_per_sample,
+                                  int n_samples) {
+  const long total = static_cast<long>(S) * M * CV;
+  for (long v = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; v < total;
+       v += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long rowg = v / CV;
+    const int s = static_cast<int>(rowg / M);
+    const long m = rowg - s * M;
+    const float f = scale[s * n_samples + m / rows_per_sample];
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(x) + v);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = pack_bf16x2(bf16lo_to_f32(w[e]) * f, bf16hi_to_f32(w[e]) * f);
+    reinterpret_cast<uint4*>(y)[v] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                           __nv_bfloat16* __restrict__ out, long n8) {
+  for (long v = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; v < n8;
+       v += static_cast<long>(gridDim.x) * blockDim.x) {
+    const uint4 qa = __ldg(reinterpret_cast<const uint4*>(a) + v);
+    const uint4 qb = __ldg(reinterpret_cast<const uint4*>(b) + v);
+    const uint32_t wa[4] = {qa.x, qa.y, qa.z, qa.w}, wb[4] = {qb.x, qb.y, qb.z, qb.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      o[e] = pack_bf16x2(bf16lo_to_f32(wa[e]) + bf16lo_to_f32(wb[e]), bf16hi_to_f32(wa[e]) + bf16hi_to_f32(wb[e]));
+    reinterpret_cast<uint4*>(out)[v] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// out[i] = sum_s x[s, i] (+ extra[i]); fp32 accumulation, bf16 in/out
+__global__ void sum_streams_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ extra,
+                                   __nv_bfloat16* __restrict__ out, int S, long n8) {
+  for (long v = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; v < n8;
+       v += static_cast<long>(gridDim.x) * blockDim.x) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s <= S; ++s) {
+      if (s == S && extra == nullptr) break;
+      const uint4 q = (s < S) ? __ldg(reinterpret_cast<const uint4*>(x) + s * n8 + v)
+                              : __ldg(reinterpret_cast<const uint4*>(extra) + v);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc[2 * e] += bf16lo_to_f32(w[e]);
+        acc[2 * e + 1] += bf16hi_to_f32(w[e]);
+      }
+    }
+    reinterpret_cast<uint4*>(out)[v] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                                  pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
+struct PackParams {
+  const float* a[8];  // [r_i, K]
+  const float* b[8];  // [N, r_i]
+  int rank[8], off[8];
+  int n, K, N, R_pad;
+  __nv_bfloat16 *a_cat, *b_cat, *a_cat_t, *b_cat_t;
+};
+
+// a_cat [R_pad, K], b_cat [N, R_pad], a_cat_t [K, R_pad], b_cat_t [R_pad, N]; zero padded.
+__global__ void pack_adapters_kernel(const PackParams p) {
+  const long nA = static_cast<long>(p.R_pad) * p.K, nB = static_cast<long>(p.N) * p.R_pad;
+  for (long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < nA + nB;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    if (idx < nA) {
+      const int r = static_cast<int>(idx / p.K), k = static_cast<int>(idx - static_cast<long>(r) * p.K);
+      float v = 0.f;
+      for (int i = 0; i < p.n; ++i)
+        if (r >= p.off[i] && r < p.off[i] + p.rank[i]) v = p.a[i][static_cast<long>(r - p.off[i]) * p.K + k];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      if (p.a_cat) p.a_cat[idx] = h;
+      if (p.a_cat_t) p.a_cat_t[static_cast<long>(k) * p.R_pad + r] = h;
+    } else {
+      const long j = idx - nA;
+      const int n = static_cast<int>(j / p.R_pad), r = static_cast<int>(j - static_cast<long>(n) * p.R_pad);
+      float v = 0.f;
+      for (int i = 0; i < p.n; ++i)
+        if (r >= p.off[i] && r < p.off[i] + p.rank[i]) v = p.b[i][static_cast<long>(n) * p.rank[i] + (r - p.off[i])];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      if (p.b_cat) p.b_cat[j] = h;
+      if (p.b_cat_t) p.b_cat_t[static_cast<long>(r) * p.N + n] = h;
+    }
+  }
+}
+
+__global__ void cast_transpose_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wb,
+                                      __nv_bfloat16* __restrict__ wt, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (r < rows && c < cols) {
+      v = w[static_cast<long>(r) * cols + c];
+      if (wb) wb[static_cast<long>(r) * cols + c] = __float2bfloat16_rn(v);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (wt) {
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int c = c0 + i, r = r0 + threadIdx.x;
+      if (r < rows && c < cols) wt[static_cast<long>(c) * rows + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    }
+  }
+}
+
+int grid_for(long work, int block) {
+  long g = (work + block - 1) / block;
+  const long cap = 148L * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace
+
+int launch_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, void* y_drop, long drop_rows,
+                         float* mean, float* rstd, long rows, int C, float eps, int merge, int H, int W, float drop_p,
+                         uint64_t drop_seed, cudaStream_t stream) {
+  MTL_REQUIRE(rows > 0 && C > 0, "layernorm: empty input");
+  MTL_REQUIRE(C % 8 == 0 && (!merge || C % 32 == 0), "layernorm: C=%d must be a multiple of 8 (32 when merging)", C);
+  MTL_REQUIRE(!merge || (H % 2 == 0 && W % 2 == 0), "patch merging: x size (%d*%d) are not even.", H, W);
+  LnFwdParams p{static_cast<const __nv_bfloat16*>(x), gamma, beta, static_cast<__nv_bfloat16*>(y),
+                static_cast<__nv_bfloat16*>(y_drop), mean, rstd, rows, drop_rows, C, merge, H, W, eps, drop_p, drop_seed};
+  const int wpb = 8;
+  layernorm_fwd_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(p);
+  MTL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                         const void* dres, void* dx, float* dgamma, float* dbeta, long rows, int C, int merge,
+                         int H, int W, cudaStream_t stream) {
+  MTL_REQUIRE(rows > 0 && C > 0, "layernorm bwd: empty input");
+  MTL_REQUIRE(C % 8 == 0 && C <= 4096, "layernorm bwd: C=%d unsupported", C);
+  MTL_REQUIRE(!(merge && dres), "layernorm bwd: residual gradient not supported together with merge");
+  LnBwdParams p{static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), gamma, mean, rstd,
+                static_cast<const __nv_bfloat16*>(dres), static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, rows, C,
+                merge, H, W, 0};
+  long ctas = 148L * 4;
+  long rpc = (rows + ctas - 1) / ctas;
+  if (rpc < 8) rpc = 8;
+  p.rows_per_cta = static_cast<int>(rpc);
+  const unsigned grid = static_cast<unsigned>((rows + rpc - 1) / rpc);
+  if (C <= 1024) layernorm_bwd_kernel<true><<<grid, 256, 2 * C * sizeof(float), stream>>>(p);
+  else layernorm_bwd_kernel<false><<<grid, 256, 2 * C * sizeof(float), stream>>>(p);
+  MTL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int launch_window_gather(const void* in, void* out, int B, int H, int W, int C, int shift, int ws,
+                                int elem_size, int scatter, cudaStream_t stream) {
+  MTL_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, "window_process: empty input");
+  MTL_REQUIRE(ws > 0 && H % ws == 0 && W % ws == 0, "window_process: H,W (%d,%d) not divisible by window %d", H, W, ws);
+  MTL_REQUIRE(elem_size == 2 || elem_size == 4, "window_process: element size %d unsupported", elem_size);
+  const long row_bytes = static_cast<long>(C) * elem_size;
+  const bool v16 = row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(in) % 16 == 0) &&
+                   (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+  if (v16) {
+    const int CV = static_cast<int>(row_bytes / 16);
+    const long total = static_cast<long>(B) * H * W * CV;
+    window_gather_kernel<uint4><<<grid_for(total, 256), 256, 0, stream>>>(
+        static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, CV, shift, ws, scatter);
+  } else if (elem_size == 4) {
+    const long total = static_cast<long>(B) * H * W * C;
+    window_gather_kernel<uint32_t><<<grid_for(total, 256), 256, 0, stream>>>(
+        static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), B, H, W, C, shift, ws, scatter);
+  } else {
+    const long total = static_cast<long>(B) * H * W * C;
+    window_gather_kernel<uint16_t><<<grid_for(total, 256), 256, 0, stream>>>(
+        static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), B, H, W, C, shift, ws, scatter);
+  }
+  MTL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// roll(-shift) + partition (inverse = its adjoint: un-partition + roll(+shift))
+int launch_roll_partition(const void* in, void* out, int B, int H, int W, int C, int shift, int ws, int elem_size,
+                          int inverse, cudaStream_t stream) {
+  return launch_window_gather(in, out, B, H, W, C, shift, ws, elem_size, inverse, stream);
+}
+// window_reverse + roll(+shift) (inverse = its adjoint: roll(-shift) + partition)
+int launch_merge_roll(const void* in, void* out, int B, int H, int W, int C, int shift, int ws, int elem_size,
+                      int inverse, cudaStream_t stream) {
+  return launch_window_gather(in, out, B, H, W, C, shift, ws, elem_size, !inverse, stream);
+}
+
+int launch_dropout(const void* x, void* y, long n, float p, uint64_t seed, cudaStream_t stream) {
+  MTL_REQUIRE(n % 8 == 0, "dropout: element count %ld must be a multiple of 8", n);
+  MTL_REQUIRE(p >= 0.f && p < 1.f, "dropout probability has to be in [0, 1), but got %f", p);
+  if (n == 0) return 0;
+  dropout_kernel<<<grid_for(n / 8, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x),
+                                                          static_cast<__nv_bfloat16*>(y), n / 8, p, seed);
+  MTL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_scale_rows(const void* x, const float* scale, void* y, int S, long M, int C, int rows_per_sample,
+                      cudaStream_t stream) {
+  MTL_REQUIRE(C % 8 == 0 && rows_per_sample > 0 && M % rows_per_sample == 0, "scale_rows: bad shape");
+  const long total = static_cast<long>(S) * M * (C / 8);
+  if (total == 0) return 0;
+  scale_rows_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), scale,
+                                                             static_cast<__nv_bfloat16*>(y), S, M, C / 8,
+                                                             rows_per_sample, static_cast<int>(M / rows_per_sample));
+  MTL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_add(const void* a, const void* b, void* out, long n, cudaStream_t stream) {
+  MTL_REQUIRE(n % 8 == 0, "add: element count %ld must be a multiple of 8", n);
+  if (n == 0) return 0;
+  add_kernel<<<grid_for(n / 8, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(a),
+                                                      static_cast<const __nv_bfloat16*>(b),
+                                                      static_cast<__nv_bfloat16*>(out), n / 8);
+  MTL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_sum_streams(const void* x, const void* extra, void* out, int S, long n, cudaStream_t stream) {
+  MTL_REQUIRE(n % 8 == 0, "sum_streams: element count %ld must be a multiple of 8", n);
+  if (n == 0) return 0;
+  sum_streams_kernel<<<grid_for(n / 8, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x),
+                                                              static_cast<const __nv_bfloat16*>(extra),
+                                                              static_cast<__nv_bfloat16*>(out), S, n / 8);
+  MTL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_pack_adapters(const float* const* a_ptrs, const float* const* b_ptrs, const int* ranks, const int* offs,
+                         int n_adapt, int K, int N, int R_pad, void* a_cat, void* b_cat, void* a_cat_t, void* b_cat_t,
+                         cudaStream_t stream) {
+  MTL_REQUIRE(n_adapt >= 1 && n_adapt <= 8, "pack: adapter count %d out of range", n_adapt);
+  PackParams p;
+  for (int i = 0; i < 8; ++i) {
+    p.a[i] = i < n_adapt ? a_ptrs[i] : nullptr;
+    p.b[i] = i < n_adapt ? b_ptrs[i] : nullptr;
+    p.rank[i] = i < n_adapt ? ranks[i] : 0;
+    p.off[i] = i < n_adapt ? offs[i] : 0;
+    if (i < n_adapt) MTL_REQUIRE(offs[i] + ranks[i] <= R_pad, "pack: adapter %d exceeds R_pad", i);
+  }
+  p.n = n_adapt; p.K = K; p.N = N; p.R_pad = R_pad;
+  p.a_cat = static_cast<__nv_bfloat16*>(a_cat);
+  p.b_cat = static_cast<__nv_bfloat16*>(b_cat);
+  p.a_cat_t = static_cast<__nv_bfloat16*>(a_cat_t);
+  p.b_cat_t = static_cast<__nv_bfloat16*>(b_cat_t);
+  const long total = static_cast<long>(R_pad) * (K + N);
+  pack_adapters_kernel<<<grid_for(total, 256), 256, 0, stream>>>(p);
+  MTL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_cast_transpose(const float* w, void* w_bf16, void* wt_bf16, int rows, int cols, cudaStream_t stream) {
+  MTL_REQUIRE(rows > 0 && cols > 0, "cast_transpose: empty matrix");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  cast_transpose_kernel<<<grid, block, 0, stream>>>(w, static_cast<__nv_bfloat16*>(w_bf16),
+                                                   static_cast<__nv_bfloat16*>(wt_bf16), rows, cols);
+  MTL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace mtl

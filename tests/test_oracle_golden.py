@@ -1,0 +1,167 @@
+"""Pins oracle/mtlora_oracle.py against vectors produced by the unmodified reference (tools/make_golden.py).
+CPU only. Tolerances are fp32 round-off: both sides run the same math in a different op order."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import detgen
+from oracle import mtlora_oracle as O
+
+TASKS = ["normals", "semseg"]
+TSCALE = {"normals": 2.0, "semseg": 3.0}
+
+
+def close(a, b, rtol=2e-5, atol=2e-6):
+    a = a.detach().double().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    scale = max(np.abs(b).max(), 1e-30)
+    err = np.abs(a - b).max()
+    assert err <= atol + rtol * scale, f"max abs err {err:.3e} vs scale {scale:.3e}"
+
+
+def det_module_params(tag, names_shapes):
+    return {n: detgen.param_value(tag + "." + n, s).requires_grad_() for n, s in names_shapes.items()}
+
+
+def lin_shapes(K, N, r, tasks):
+    s = {}
+    if r["shared"] > 0:
+        s["lora_shared_A"], s["lora_shared_B"] = (r["shared"], K), (N, r["shared"])
+    s["linear.weight"], s["linear.bias"] = (N, K), (N,)
+    if tasks and r["shared"] > 0:
+        for t in tasks:
+            s["lora_tasks_A." + t], s["lora_tasks_B." + t] = (r[t], K), (N, r[t])
+    return s
+
+
+@pytest.mark.parametrize("tag,K,N,r,use_tasks,xt", [
+    ("lin_shared", 96, 288, {"shared": 8}, False, False),
+    ("lin_tasks", 96, 96, {"shared": 16, "normals": 4, "semseg": 4}, True, False),
+    ("lin_xtasks", 96, 384, {"shared": 16, "normals": 4, "semseg": 8}, True, True),
+    ("lin_r0", 64, 48, {"shared": 0}, False, False),
+])
+def test_mtlora_linear(golden, tag, K, N, r, use_tasks, xt):
+    p = det_module_params(tag, lin_shapes(K, N, r, TASKS if use_tasks else None))
+    x = detgen.uniform(tag + ".x", (2, 49, K)).requires_grad_()
+    x_tasks = {t: detgen.uniform(f"{tag}.x.{t}", (2, 49, K)).requires_grad_() for t in TASKS} if xt else None
+    y, yt = O.mtlora_linear(p, "", x, x_tasks, TASKS if use_tasks else None, 4.0, TSCALE)
+    loss = (y * detgen.uniform(tag + ".gy", tuple(y.shape))).sum()
+    if use_tasks:
+        assert yt is not None and list(yt) == TASKS
+        for t in TASKS:
+            loss = loss + (yt[t] * detgen.uniform(f"{tag}.gy.{t}", tuple(y.shape))).sum()
+    else:
+        assert yt is None
+    loss.backward()
+    close(y, golden[tag + "/y"])
+    if use_tasks:
+        for t in TASKS:
+            close(yt[t], golden[f"{tag}/y.{t}"])
+    close(x.grad, golden[tag + "/dx"])
+    if xt:
+        for t in TASKS:
+            close(x_tasks[t].grad, golden[f"{tag}/dx.{t}"])
+    for n, v in p.items():
+        if "lora" in n:
+            close(v.grad, golden[f"{tag}/d.{n}"], rtol=5e-5)
+
+
+@pytest.mark.parametrize("tag,B,H,W,C,shift,ws", [("win_s2", 2, 14, 14, 8, 2, 7), ("win_s3", 1, 28, 14, 4, 3, 7)])
+def test_window_process_bitwise(golden, tag, B, H, W, C, shift, ws):
+    """The reference's only unit test (kernels/window_process/unit_test.py) asserts bitwise equality."""
+    x = detgen.uniform(tag + ".x", (B, H, W, C))
+    part = O.roll_window_partition(x, shift, ws)
+    assert np.array_equal(part.numpy(), golden[tag + "/partition"])
+    assert torch.equal(O.window_merge_roll(part, shift, ws, H, W), x)
+    merged = O.window_merge_roll(x.reshape(-1, ws, ws, C), shift, ws, H, W)
+    assert np.array_equal(merged.numpy(), golden[tag + "/merge_of_x"])
+
+
+def block_shapes(lora, ws):
+    r = {"shared": 8, "normals": 4, "semseg": 4}
+    s = {"norm1.weight": (96,), "norm1.bias": (96,), "attn.relative_position_bias_table": ((2 * ws - 1) ** 2, 3)}
+    for pre, K, N, t in [("attn.qkv.", 96, 288, False), ("attn.proj.", 96, 96, lora)]:
+        s.update({pre + k: v for k, v in lin_shapes(K, N, r, TASKS if t else None).items()})
+    s.update({"norm2.weight": (96,), "norm2.bias": (96,)})
+    for pre, K, N in [("mlp.fc1.", 96, 384), ("mlp.fc2.", 384, 96)]:
+        s.update({pre + k: v for k, v in lin_shapes(K, N, r, TASKS if lora else None).items()})
+    return s
+
+
+@pytest.mark.parametrize("tag,H,shift,lora", [("blk_s0", 14, 0, False), ("blk_s3_lora", 14, 3, True),
+                                             ("blk_s0_lora", 14, 0, True), ("blk_small", 7, 3, True)])
+def test_swin_block(golden, tag, H, shift, lora):
+    p = det_module_params(tag, block_shapes(lora, 7))
+    cfg = O.OracleConfig(tasks=tuple(TASKS), shared_scale=(4.0,), task_scale=[{t: 4.0 for t in TASKS}], dropout=(0.0,))
+    x = detgen.uniform(tag + ".x", (2, H * H, 96)).requires_grad_()
+    y, yt = O.swin_block(p, "", x, H, H, 3, 7, shift, cfg, 0, lora)
+    loss = (y * detgen.uniform(tag + ".gy", tuple(y.shape))).sum()
+    if lora:
+        for t in TASKS:
+            loss = loss + (yt[t] * detgen.uniform(f"{tag}.gy.{t}", tuple(y.shape))).sum()
+    loss.backward()
+    close(y, golden[tag + "/y"], rtol=5e-5)
+    if lora:
+        for t in TASKS:
+            close(yt[t], golden[f"{tag}/y.{t}"], rtol=5e-5)
+    close(x.grad, golden[tag + "/dx"], rtol=1e-4)
+    for n, v in p.items():
+        key = f"{tag}/d.{n}"
+        if key in golden.files:
+            close(v.grad, golden[key], rtol=2e-4)
+    ws_eff = min(7, H)
+    assert np.array_equal(O.relative_position_index(ws_eff).numpy(), golden[tag + "/relative_position_index"])
+    if tag + "/attn_mask" in golden.files:
+        assert np.array_equal(O.shift_attn_mask(H, H, 7, shift).numpy(), golden[tag + "/attn_mask"])
+
+
+@pytest.mark.parametrize("tag,ds", [("pm_dense", False), ("pm_lora", True)])
+def test_patch_merging(golden, tag, ds):
+    if ds:
+        s = {"reduction." + k: v for k, v in lin_shapes(384, 192, {"shared": 8}, None).items() if "bias" not in k}
+    else:
+        s = {"reduction.weight": (192, 384)}
+    s.update({"norm.weight": (384,), "norm.bias": (384,)})
+    p = det_module_params(tag, s)
+    cfg = O.OracleConfig(shared_scale=(4.0,), dropout=(0.0,))
+    x = detgen.uniform(tag + ".x", (2, 196, 96)).requires_grad_()
+    y = O.patch_merging(p, "", x, 14, 14, cfg, 0)
+    (y * detgen.uniform(tag + ".gy", tuple(y.shape))).sum().backward()
+    close(y, golden[tag + "/y"])
+    close(x.grad, golden[tag + "/dx"], rtol=5e-5)
+    for n, v in p.items():
+        close(v.grad, golden[f"{tag}/d.{n}"], rtol=1e-4)
+
+
+def sample(t, stride=101):
+    f = t.detach().reshape(-1).double()
+    return np.concatenate([[f.sum().item(), f.abs().sum().item(), float(f.numel())], f[::stride].numpy()])
+
+
+def test_backbone_config1(golden):
+    """BASELINE.json configs[0]: Swin-T 224, 1 task (semseg), r = 4, batch 2, CPU fwd+bwd."""
+    cfg = O.OracleConfig(img_size=224, tasks=("semseg",))
+    ranks = [{"shared": 4, "semseg": 4}] * 4
+    p = {k: v.requires_grad_() for k, v in detgen.make_params(detgen.backbone_param_shapes(cfg, ranks)).items()}
+    img = detgen.uniform("c1.img", (2, 3, 224, 224), -2.0, 2.0)
+    stages = O.backbone(p, img, cfg)
+    loss = O.backbone_loss(stages)
+    loss.backward()
+    assert abs(loss.item() - golden["c1/loss"][0]) <= 1e-4 * abs(golden["c1/loss"][0])
+    for s, (xs, tl) in enumerate(stages):
+        for name, t in ((f"c1/stage{s}.x", xs), (f"c1/stage{s}.semseg", tl["semseg"])):
+            g = golden[name]
+            got = sample(t)
+            assert got[2] == g[2]
+            close(got[3:], g[3:], rtol=2e-4)
+            assert abs(got[1] - g[1]) <= 1e-4 * g[1]
+    none = sorted(n for n, v in p.items() if v.grad is None)
+    assert none == sorted(golden["c1/none_grads"].tolist())
+    checked = 0
+    for n, v in p.items():
+        key = f"c1/d.{n}"
+        if key in golden.files:
+            close(sample(v.grad, 53)[3:], golden[key][3:], rtol=1e-3)
+            checked += 1
+    assert checked > 150
