@@ -94,15 +94,17 @@ int mtl_linear_fwd(const mtl_linear_cfg* cfg, const void* x, const void* w_bf16,
  *   dx[t] = G_t A_t                                      (only if x_tasks_given)
  * dy:       [1+T, M, N];  dx: [1 (+T if x_tasks_given), M, K]
  * gelu_aux: optional, same shape as dx: dx *= GELU'(gelu_aux)  (the producer of x was the fused GELU epilogue)
- * path_scale: optional per-stream per-sample scale of dy rows (DropPath backward); supported in-kernel only for
- *        T == 0 — with task streams pre-scale dy with mtl_scale_rows.
- * g_save:   [M, R] bf16, optional: G kept for mtl_linear_bwd_params. */
+ * path_scale: optional per-sample scale of dy rows (DropPath backward); supported in-kernel only for a layer
+ *        with a single output stream — with task streams pre-scale dy with mtl_scale_rows and pass NULL here and
+ *        to mtl_linear_bwd_params.
+ * g_save:   [M, R] bf16, optional: G (without path_scale) kept for mtl_linear_bwd_params. */
 int mtl_linear_bwd_input(const mtl_linear_cfg* cfg, const void* dy, const void* wt_bf16, const void* a_cat_t,
                          const void* b_cat_t, void* dx, const void* gelu_aux, const float* path_scale,
                          void* g_save, mtl_stream_t stream);
 
 /* Adapter gradients, accumulated into packed fp32 buffers da_cat [R, K] and db_cat [N, R]:
- *   dB_s += dy[s]^T U_s,   dA_s += G_s^T x_in(s)       (x_in(s): the stream adapter s consumed in forward)
+ *   dB_s += dy[s]^T (ps[s] U_s),   dA_s += G_s^T (ps[s] x_in(s))   (x_in(s): the stream adapter s consumed in forward;
+ *   ps = path_scale [1+T, M / rows_per_sample] or NULL)
  * x is the forward input (same layout incl. the dropped copy); x_gelu != 0 applies GELU to x on load (x is then
  * the saved fc1 pre-activation, i.e. the fc2 input is recomputed instead of stored). */
 int mtl_linear_bwd_params(const mtl_linear_cfg* cfg, const void* x, int32_t x_gelu, const void* dy,

@@ -285,9 +285,9 @@ int mtl_linear_bwd_input(const mtl_linear_cfg* cfg, const void* dy, const void* 
     MTL_REQUIRE(p.S_in == 1, "linear_bwd_input: in-kernel path_scale needs a single dy stream; pre-scale dy instead");
     MTL_REQUIRE(cfg->rows_per_sample > 0 && cfg->M % cfg->rows_per_sample == 0,
                 "linear_bwd_input: rows_per_sample=%d does not divide M=%lld", cfg->rows_per_sample, (long long)cfg->M);
-    // a single stream: scaling the rows of dy == scaling the rows of the result
+    // a single stream: scaling the rows of dy == scaling the rows of the result. The saved G stays unscaled;
+    // mtl_linear_bwd_params applies the same path_scale to its second operand.
     p.rowscale_out = path_scale;
-    p.rowscale_in = path_scale;  // keeps the saved G consistent (G = s * ps * dy B)
     p.rows_per_sample = cfg->rows_per_sample;
     p.n_samples = static_cast<int>(cfg->M / cfg->rows_per_sample);
   }
@@ -333,10 +333,11 @@ int mtl_linear_bwd_params(const mtl_linear_cfg* cfg, const void* x, int32_t x_ge
                            N, L.len[a], path_scale ? path_scale + static_cast<size_t>(a) * n_samples : nullptr,
                            cfg->rows_per_sample, 0, 1.f, S(stream)))
       return e;
-    // dA_a [len, K] += G[:, off:off+len]^T x_in(a)     (G already carries scale and path scale)
+    // dA_a [len, K] += G[:, off:off+len]^T (ps[a] * x_in(a))     (G carries the adapter scale, not the path scale)
     if (int e = launch_xty(gb + L.off[a], L.R_pad, xb + static_cast<size_t>(in) * M * K, K,
-                           da_cat + static_cast<size_t>(L.off[a]) * K, K, M, L.len[a], K, nullptr, 0, x_gelu, 1.f,
-                           S(stream)))
+                           da_cat + static_cast<size_t>(L.off[a]) * K, K, M, L.len[a], K,
+                           path_scale ? path_scale + static_cast<size_t>(a) * n_samples : nullptr, cfg->rows_per_sample,
+                           x_gelu, 1.f, S(stream)))
       return e;
   }
   return 0;

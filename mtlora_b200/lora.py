@@ -1,0 +1,338 @@
+"""Host-side mirror of the reference's `models/lora.py` for the hot path: `MTLoRALinear` (reference :159-284),
+`LoRALayer` (:62-84), `mark_only_lora_as_trainable` (:580-630) and `map_old_state_dict_weights` (:644-668).
+
+Same constructor arguments, parameter names / shapes / registration order (checkpoint surface), `(tensor,
+dict | None)` return convention and error behaviour as the reference; the arithmetic runs in
+libmtlora_b200.so (`mtl_linear_fwd` / `mtl_linear_bwd_input` / `mtl_linear_bwd_params`, include/mtlora_b200.h) in
+bf16 with fp32 accumulation. There is no PyTorch fallback: CPU tensors raise.
+"""
+import math
+from typing import Any, Dict, Mapping, Optional, Union
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+BF16 = torch.bfloat16
+
+
+class LoRALayer(nn.Module):
+    """Reference models/lora.py:62-84: stores r, the scale ("lora_alpha") and the LoRA-branch dropout."""
+
+    def __init__(self, r: int, lora_alpha: float, lora_dropout: float):
+        super().__init__()
+        assert r >= 0
+        self.r = r
+        self.lora_alpha = lora_alpha
+        self.lora_dropout_p = float(lora_dropout)
+        self.lora_dropout = nn.Dropout(p=lora_dropout) if lora_dropout > 0.0 else (lambda x: x)
+        self.merged = False
+
+
+def _new_seed():
+    """Seed of the counter-based dropout mask, drawn from torch's CPU generator (so torch.manual_seed governs it)."""
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+class LinearEngine:
+    """Per-layer staging + explicit forward / backward over the C ABI (not an autograd object).
+
+    Used by `MTLoRALinear` / `CompatLinear` standalone (through `_LinearFn`) and by the fused block / patch-merging
+    functions in swin_transformer_mtlora.py, which call `forward` / `backward` directly from their own backward.
+    """
+
+    def __init__(self, owner, linear: nn.Linear, spec: ops.LinearSpec, tasks):
+        self.owner = owner          # the nn.Module holding lora_* parameters (or None for a plain linear)
+        self.linear = linear
+        self.spec = spec
+        self.tasks = list(tasks) if tasks else []
+        self._wkey = None
+        self._w = self._wt = None
+        self._akey = None
+        self._packed = (None, None, None, None)
+
+    # ---- parameter staging -------------------------------------------------------------------------------------
+    def adapters(self):
+        o = self.owner
+        if self.spec.r_shared == 0:
+            return []
+        ps = [o.lora_shared_A, o.lora_shared_B]
+        ps += [o.lora_tasks_A[t] for t in self.tasks] + [o.lora_tasks_B[t] for t in self.tasks]
+        return ps
+
+    def params(self):
+        """Parameters in the order `backward` reports gradients: weight, bias?, shared A, B, task A..., task B..."""
+        lin = self.linear
+        return [lin.weight] + ([lin.bias] if lin.bias is not None else []) + self.adapters()
+
+    def stage(self):
+        w = self.linear.weight
+        if not w.is_cuda:
+            raise RuntimeError("mtlora_b200: parameters must live on a CUDA device — there is no CPU path")
+        key = (w.data_ptr(), w._version)
+        if key != self._wkey:
+            with torch.no_grad():
+                self._w, self._wt = ops.cast_transpose(w.detach().float().contiguous())
+            self._wkey = key
+        if self.spec.r_shared > 0:
+            ad = self.adapters()
+            akey = tuple((p.data_ptr(), p._version) for p in ad)
+            if akey != self._akey:
+                T = len(self.tasks)
+                with torch.no_grad():
+                    d = [p.detach().float().contiguous() for p in ad]
+                    self._packed = ops.pack_adapters(self.spec, d[0], d[1], d[2:2 + T], d[2 + T:2 + 2 * T])
+                self._akey = akey
+        return self._w, self._wt, self._packed
+
+    # ---- explicit forward / backward ---------------------------------------------------------------------------
+    def forward(self, x, *, xt=False, gelu=False, residual=None, path_scale=None, rows_per_sample=0, dropout_p=0.0,
+                seed=0, save=True):
+        """x [S_in, M, K] bf16 (incl. the appended D(x[0]) stream when dropout_p > 0) -> y, y_act, saved-dict."""
+        w, _, (a_cat, b_cat, _, _) = self.stage()
+        bias = self.linear.bias
+        bias = None if bias is None else bias.detach().float()
+        y, y_act, u = ops.linear_fwd(self.spec, x, w, bias, a_cat, b_cat, x_tasks_given=xt, act_gelu=gelu,
+                                     residual=residual, path_scale=path_scale, rows_per_sample=rows_per_sample,
+                                     dropout_p=dropout_p, seed=seed, save_u=save)
+        saved = None
+        if save:
+            saved = dict(x=x, u=u, xt=xt, dropout_p=dropout_p, seed=seed, path_scale=path_scale,
+                         rows_per_sample=rows_per_sample)
+        return y, y_act, saved
+
+    def backward(self, saved, dy, *, gelu_aux=None, need_dx=True):
+        """dy [S_out, M, N] -> dx [1 (+T), M, K], {param: fp32 grad} for every parameter that requires grad.
+
+        DropPath (`path_scale` given in forward): a single-stream layer scales inside the kernels, a multi-stream
+        layer pre-scales dy once (header contract of mtl_linear_bwd_input)."""
+        spec = self.spec
+        _, wt, (_, _, a_cat_t, b_cat_t) = self.stage()
+        ps, rps = saved["path_scale"], saved["rows_per_sample"]
+        if ps is not None and spec.S_out > 1:
+            dy = ops.scale_rows(dy, ps, rps)
+            ps = None
+        lin = self.linear
+        ad = self.adapters()
+        want_ad = any(p.requires_grad for p in ad)
+        dx, g = ops.linear_bwd_input(spec, dy, wt, a_cat_t, b_cat_t, x_tasks_given=saved["xt"], gelu_aux=gelu_aux,
+                                     path_scale=ps, rows_per_sample=rps if ps is not None else 0,
+                                     dropout_p=saved["dropout_p"], seed=saved["seed"], save_g=want_ad)
+        grads = {}
+        if want_ad:
+            da, db = ops.linear_bwd_params(spec, saved["x"], dy, saved["u"], g, x_tasks_given=saved["xt"],
+                                           path_scale=ps, rows_per_sample=rps if ps is not None else 0,
+                                           dropout_p=saved["dropout_p"])
+            T = len(self.tasks)
+            for i in range(1 + T):
+                off, r = spec.offsets[i], spec.ranks[i]
+                pa = ad[0] if i == 0 else ad[2 + (i - 1)]
+                pb = ad[1] if i == 0 else ad[2 + T + (i - 1)]
+                if pa.requires_grad:
+                    grads[pa] = da[off:off + r]
+                if pb.requires_grad:
+                    grads[pb] = db[:, off:off + r]
+        if lin.weight.requires_grad or (lin.bias is not None and lin.bias.requires_grad):
+            # trainable dense weight (PatchMerging.reduction under plain MTLoRA, lora.py:599-600; or an unfrozen layer):
+            # dW = dPre^T x[0], dbias = column sums of dPre, dPre = sum_j dy[j] (lora.py:255,262-266)
+            M = dy.shape[1]
+            dpre = dy[0] if dy.shape[0] == 1 else ops.sum_streams(dy)
+            if ps is not None:
+                dpre = ops.scale_rows(dpre.unsqueeze(0), ps[:1].contiguous(), rps)[0]
+            if lin.weight.requires_grad:
+                grads[lin.weight] = ops.xty(dpre, saved["x"][0])
+            if lin.bias is not None and lin.bias.requires_grad:
+                ones = torch.ones((M, 8), dtype=BF16, device=dy.device)
+                grads[lin.bias] = ops.xty(dpre, ones)[:, 0]
+        return dx, grads
+
+
+class _LinearFn(torch.autograd.Function):
+    """Autograd wrapper for a stand-alone MTLoRALinear / CompatLinear call (the fused block has its own)."""
+
+    @staticmethod
+    def forward(ctx, engine, xt, dropout_p, seed, x, *params):
+        ctx.engine = engine
+        need = any(ctx.needs_input_grad[4:])
+        y, _, saved = engine.forward(x, xt=xt, dropout_p=dropout_p, seed=seed, save=need)
+        ctx.saved = saved
+        ctx.params = params
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        eng = ctx.engine
+        dx, grads = eng.backward(ctx.saved, dy.contiguous())
+        if ctx.saved["dropout_p"] > 0 and eng.spec.r_shared > 0:
+            # the appended D(x[0]) stream is produced from x[0] inside the wrapper; its gradient is folded into dx[0]
+            pad = torch.zeros_like(dx[:1])
+            dx = torch.cat([dx, pad]) if dx.shape[0] + 1 == ctx.saved["x"].shape[0] else dx
+        return (None, None, None, None, dx) + tuple(grads.get(p) for p in ctx.params)
+
+
+def run_linear_standalone(engine, x, x_tasks, dropout_p, training):
+    """Common stand-alone call path: arbitrary leading shape (..., K) -> ((..., N), {task: (..., N)} | None)."""
+    if not x.is_cuda:
+        raise RuntimeError("mtlora_b200: expected CUDA tensors — there is no CPU path (build + run on the B200)")
+    spec = engine.spec
+    lead, K = x.shape[:-1], x.shape[-1]
+    if K != spec.K:
+        raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({x.numel() // max(K, 1)}x{K} and {spec.K}x{spec.Nf})")
+    in_dtype = x.dtype
+    M = x.numel() // K
+    streams = [x.reshape(M, K).to(BF16)]
+    xt = x_tasks is not None and spec.T > 0
+    if xt:
+        streams += [x_tasks[t].reshape(M, K).to(BF16) for t in engine.tasks]
+    p = dropout_p if (training and spec.r_shared > 0) else 0.0
+    seed = _new_seed() if p > 0 else 0
+    if p > 0:
+        streams.append(_DropoutFn.apply(streams[0], p, seed))
+    xs = torch.stack(streams)
+    y = _LinearFn.apply(engine, xt, p, seed, xs, *engine.params())
+    outs = [y[i].reshape(*lead, spec.Nf).to(in_dtype) for i in range(spec.S_out)]
+    if spec.S_out == 1 and not (spec.r_shared > 0 and engine.tasks):
+        return outs[0], None
+    return outs[0], {t: outs[1 + i] for i, t in enumerate(engine.tasks)}
+
+
+class _DropoutFn(torch.autograd.Function):
+    """D(x) with the library's counter-based mask (mtl_dropout); backward re-applies the same mask."""
+
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        ctx.p, ctx.seed = p, seed
+        return ops.dropout(x.contiguous(), p, seed)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.dropout(dy.contiguous(), ctx.p, ctx.seed), None, None
+
+
+class MTLoRALinear(LoRALayer):
+    """Frozen nn.Linear + one task-shared and T task-specific low-rank updates (reference models/lora.py:159-284).
+
+    forward(x, x_tasks=None) -> (pretrained + shared_lora(x), {task: pretrained + task_lora(x or x_tasks[task])} | None)
+    """
+
+    def __init__(self, in_features: int, out_features: int, r: Union[int, Mapping[str, int]] = 0,
+                 lora_shared_scale: float = 1.0, lora_task_scale: Union[float, Mapping[str, float]] = 1.0,
+                 lora_dropout: float = 0.0, tasks=None, trainable_scale_shared=False, trainable_scale_per_task=False,
+                 shared_mode: str = "matrix", **kwargs):
+        assert shared_mode in ["matrix", "matrixv2", "add", "addition", "lora_only"]
+        if shared_mode == "add":
+            shared_mode = "addition"
+        if shared_mode == "lora_only":
+            tasks = None
+        has_tasks = tasks is not None
+        if not has_tasks and shared_mode not in ["matrix"]:
+            shared_mode = "matrix"
+        if shared_mode != "matrix":
+            raise NotImplementedError(
+                f"mtlora_b200: shared_mode={shared_mode!r} is not implemented yet (every shipped YAML uses 'matrix')")
+        if trainable_scale_shared or trainable_scale_per_task:
+            raise NotImplementedError("mtlora_b200: trainable LoRA scales are not implemented yet")
+        if isinstance(r, int):
+            r = {"shared": r}
+        super().__init__(r=r["shared"], lora_alpha=lora_shared_scale, lora_dropout=lora_dropout)
+        self.linear = nn.Linear(in_features, out_features, **kwargs)
+        self.tasks = tasks
+        self.shared_mode = shared_mode
+        r_tasks, s_tasks = [], []
+        if r["shared"] > 0:
+            if has_tasks:
+                self.lora_tasks_A = nn.ParameterDict({
+                    task: nn.Parameter(self.linear.weight.new_zeros((r[task], in_features))) for task in tasks})
+                self.lora_tasks_B = nn.ParameterDict({
+                    task: nn.Parameter(self.linear.weight.new_zeros((out_features, r[task]))) for task in tasks})
+                self.lora_task_scale = {task: lora_task_scale[task] for task in tasks}
+                r_tasks = [r[t] for t in tasks]
+                s_tasks = [float(self.lora_task_scale[t]) for t in tasks]
+            self.lora_shared_A = nn.Parameter(self.linear.weight.new_zeros((r["shared"], in_features)))
+            self.lora_shared_B = nn.Parameter(self.linear.weight.new_zeros((out_features, r["shared"])))
+            self.lora_shared_scale = lora_shared_scale
+            self.reset_parameters()
+        spec = ops.LinearSpec(in_features, out_features, r["shared"], r_tasks, float(lora_shared_scale), s_tasks)
+        self._engine = LinearEngine(self, self.linear, spec, tasks if (has_tasks and r["shared"] > 0) else None)
+
+    @property
+    def engine(self):
+        return self._engine
+
+    def reset_parameters(self):
+        """A ~ kaiming_uniform(a=sqrt(5)), B = 0 (reference :236-247): the layer starts equal to the frozen linear."""
+        if hasattr(self, "lora_shared_A"):
+            nn.init.kaiming_uniform_(self.lora_shared_A, a=math.sqrt(5))
+            nn.init.zeros_(self.lora_shared_B)
+        if hasattr(self, "lora_tasks_A"):
+            for task in self.tasks:
+                nn.init.kaiming_uniform_(self.lora_tasks_A[task], a=math.sqrt(5))
+                nn.init.zeros_(self.lora_tasks_B[task])
+
+    def merge(self):
+        raise NotImplementedError
+
+    def forward(self, x: torch.Tensor, x_tasks: Optional[Dict[str, torch.Tensor]] = None):
+        return run_linear_standalone(self._engine, x, x_tasks, self.lora_dropout_p, self.training)
+
+
+def mark_only_lora_as_trainable(model: nn.Module, bias: str = "none", freeze_patch_embed: bool = False,
+                                freeze_norm: bool = False, free_relative_bias: bool = False,
+                                freeze_downsample_reduction=False) -> None:
+    """Freeze everything except LoRA parameters and the optional extras, by substring match on parameter names
+    (reference models/lora.py:580-630; NB `free_relative_bias` means *freeze* there, kept for drop-in parity)."""
+    def keep(name):
+        return ("lora_" in name
+                or (not freeze_patch_embed and "patch_embed" in name)
+                or (not freeze_norm and "norm" in name)
+                or (not freeze_downsample_reduction and "downsample.reduction" in name)
+                or (not free_relative_bias and "relative_position_bias_table" in name))
+
+    print(f"LoRA bias mode: {bias}")
+    print(f"LoRA Freeze patch_embed: {freeze_patch_embed}")
+    print(f"LoRA Freeze norm: {freeze_norm}")
+    print(f"LoRA Freeze downsample_reduction: {freeze_downsample_reduction}")
+    print(f"LoRA Freeze relative_position_bias: {free_relative_bias}")
+    for n, p in model.named_parameters():
+        if not keep(n):
+            p.requires_grad = False
+    if bias == "none":
+        return
+    if bias == "all":
+        for n, p in model.named_parameters():
+            if "bias" in n:
+                p.requires_grad = True
+    elif bias == "lora_only":
+        for m in model.modules():
+            if isinstance(m, LoRALayer) and hasattr(m, "bias") and m.bias is not None:
+                m.bias.requires_grad = True
+    else:
+        raise NotImplementedError
+
+
+def lora_filter(key: str, value: Any) -> bool:
+    return "lora_" in key
+
+
+def map_old_state_dict_weights(state_dict: Dict, mapping: Mapping, prefix: str, split_qkv: bool = False) -> Dict:
+    """Rename checkpoint keys (e.g. `attn.qkv.weight` -> `attn.qkv.linear.weight`), reference :644-668."""
+    missing = []
+    for old, new in mapping.items():
+        src = prefix + old
+        if src not in state_dict:
+            missing.append(old)
+            continue
+        dst = prefix + new
+        value = state_dict.pop(src)
+        tail = ".".join(dst.split(".")[-4:])
+        if split_qkv and tail in ("attn.qkv.linear.weight", "attn.qkv.linear.bias"):
+            kind = tail.split(".")[-1]
+            stem = ".".join(dst.split(".")[:-2])
+            for part, chunk in zip("qkv", torch.chunk(value, chunks=3)):
+                state_dict[f"{stem}.{part}.linear.{kind}"] = chunk
+        else:
+            state_dict[dst] = value
+    if missing:
+        print(f"WARNING: The following keys from the checkpoint were not mapped: {missing}")
+    return state_dict
