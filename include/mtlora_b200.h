@@ -33,6 +33,9 @@ enum { MTL_ACT_NONE = 0, MTL_ACT_GELU = 1 };
 
 int mtl_abi_version(void);
 const char* mtl_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (all threads); bench.py reports the delta over
+ * its timed region as `gpu_launches`. */
+uint64_t mtl_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------------------
  * MTLoRALinear  — models/lora.py:159-284
@@ -79,7 +82,8 @@ int mtl_cast_transpose(const float* w, void* w_bf16, void* wt_bf16, int32_t rows
  *        produced by the upstream kernel with the same seed)
  * y:     [1+T, M, N]  (T = 0 -> a single stream)
  * act == MTL_ACT_GELU (Mlp.forward swin_transformer_mtlora.py:69-75): y keeps the pre-activation (needed by
- *        backward), y_act [1+T (+1 if dropout_p > 0), M, N] receives GELU(y) and, last, D(GELU(y[0])).
+ *        backward), y_act [1+T (+1 if dropout_p > 0), M, N] receives GELU(y) and, last, D(GELU(y[0])) drawn with
+ *        dropout_seed + 1 (the seed the consuming fc2 layer must be called with).
  * residual/res_streams/path_scale (SwinTransformerBlock.forward :389-392,398-408): when residual != NULL,
  *        y[j] = residual[res_streams == 1 ? 0 : j] + path_scale[j, sample] * (above); path_scale may be NULL (=1),
  *        layout [1+T, M / rows_per_sample] fp32 (DropPath keep-mask / keep-prob, independent per stream).

@@ -44,6 +44,7 @@ _PP = ctypes.POINTER(c_void_p)
 SIGNATURES = {
     "mtl_abi_version": (c_int, []),
     "mtl_last_error": (ctypes.c_char_p, []),
+    "mtl_launch_count": (c_uint64, []),
     "mtl_linear_rank_pad": (c_int, [_CFG_P]),
     "mtl_linear_rank_offset": (c_int, [_CFG_P, c_int]),
     "mtl_linear_pack": (c_int, [_CFG_P, c_void_p, c_void_p, _PP, _PP, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -102,16 +103,31 @@ def load():
     return lib
 
 
-def call(name, *args):
+profile = None  # set to a list to record (name, meta, start_event, end_event) for every C-ABI call (bench.py --profile-ops)
+
+
+def call(name, *args, meta=None):
     """Invoke a C-ABI function returning an int status; raise RuntimeError(mtl_last_error()) on failure."""
     global launch_count
     lib = load()
+    if profile is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.mtl_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"{name} failed (code {rc}): {msg}")
+    if profile is not None:
+        e1.record()
+        profile.append((name, meta, e0, e1))
     launch_count += 1
     return rc
+
+
+def kernel_launches():
+    """Process-wide number of CUDA kernels launched by libmtlora_b200.so (mtl_launch_count)."""
+    return int(load().mtl_launch_count())
 
 
 def ptr(t):

@@ -4,6 +4,7 @@
 #include "../../include/mtlora_b200.h"
 
 #include <stdarg.h>
+#include <atomic>
 #include <string.h>
 
 #include "kernels.cuh"
@@ -19,6 +20,9 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 namespace {
 
@@ -107,6 +111,7 @@ extern "C" {
 
 int mtl_abi_version(void) { return MTL_ABI_VERSION; }
 const char* mtl_last_error(void) { return g_err; }
+uint64_t mtl_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int mtl_linear_rank_pad(const mtl_linear_cfg* cfg) {
   RankLayout L;

@@ -472,7 +472,7 @@ int launch_win_attn_fwd(const void* qkv, const float* rpb, const float* mask, in
   int gx = n_win;
   const int cap = (148 * 8 + nH - 1) / nH;  // ~8 CTAs per SM in flight across heads
   if (gx > cap) gx = cap;
-  win_attn_fwd_kernel<<<dim3(gx, nH), 128, 0, stream>>>(p);
+  win_attn_fwd_kernel<<<dim3(gx, nH), 128, 0, stream>>>(p); note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -496,7 +496,7 @@ int launch_win_attn_bwd(const void* qkv, const void* dout, const float* rpb, con
   int gx = n_win;
   const int cap = (148 * 4 + nH - 1) / nH;
   if (gx > cap) gx = cap;
-  win_attn_bwd_kernel<<<dim3(gx, nH), 128, 0, stream>>>(p);
+  win_attn_bwd_kernel<<<dim3(gx, nH), 128, 0, stream>>>(p); note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -13,6 +13,8 @@ namespace mtl {
 // Error handling: the C ABI returns int codes, last message kept thread-local (see api.cu).
 // ---------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
+// Every kernel launch site calls this once; mtl_launch_count() (C ABI) reports the process-wide total.
+void note_launch();
 
 #define MTL_CHECK_CUDA(expr)                                                           \
   do {                                                                                 \

@@ -375,14 +375,15 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               dst2[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               dst2[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
               if (p.drop_mode == 1 && j == 0) {
-                // D(m): derived from the bf16-rounded activation so it equals dropout(y2) exactly
+                // D(m): derived from the bf16-rounded activation so it equals dropout(y2, seed + 1) exactly; the next
+                // layer (fc2) is called with dropout_seed + 1 so that its mask is independent of this layer's input mask
                 const uint32_t thr = dropout_threshold(p.drop_p);
                 const float keep_scale = 1.f / (1.f - p.drop_p);
                 const uint64_t e0 = static_cast<uint64_t>(grow) * p.Nn + n0;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                  const float lo = dropout_hash(p.drop_seed, e0 + 2 * i) >= thr ? bf16lo_to_f32(pk[i]) * keep_scale : 0.f;
-                  const float hi = dropout_hash(p.drop_seed, e0 + 2 * i + 1) >= thr ? bf16hi_to_f32(pk[i]) * keep_scale : 0.f;
+                  const float lo = dropout_hash(p.drop_seed + 1, e0 + 2 * i) >= thr ? bf16lo_to_f32(pk[i]) * keep_scale : 0.f;
+                  const float hi = dropout_hash(p.drop_seed + 1, e0 + 2 * i + 1) >= thr ? bf16hi_to_f32(pk[i]) * keep_scale : 0.f;
                   pk[i] = pack_bf16x2(lo, hi);
                 }
                 uint4* dst3 = reinterpret_cast<uint4*>(p.y2 + static_cast<size_t>(p.S_out) * stream_stride +
@@ -536,7 +537,7 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
   MTL_CHECK_CUDA(attr_err);
 
   const dim3 grid(m_tiles * p.n_splits);
-  mtl_linear_kernel<<<grid, kThreads, smem_bytes, stream>>>(tm_x, tm_w, tm_down, tm_up, p);
+  mtl_linear_kernel<<<grid, kThreads, smem_bytes, stream>>>(tm_x, tm_w, tm_down, tm_up, p); note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

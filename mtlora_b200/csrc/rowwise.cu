@@ -407,7 +407,7 @@ int launch_layernorm_fwd(const void* x, const float* gamma, const float* beta, v
   LnFwdParams p{static_cast<const __nv_bfloat16*>(x), gamma, beta, static_cast<__nv_bfloat16*>(y),
                 static_cast<__nv_bfloat16*>(y_drop), mean, rstd, rows, drop_rows, C, merge, H, W, eps, drop_p, drop_seed};
   const int wpb = 8;
-  layernorm_fwd_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(p);
+  layernorm_fwd_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(p); note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -428,6 +428,7 @@ int launch_layernorm_bwd(const void* dy, const void* x, const float* gamma, cons
   const unsigned grid = static_cast<unsigned>((rows + rpc - 1) / rpc);
   if (C <= 1024) layernorm_bwd_kernel<true><<<grid, 256, 2 * C * sizeof(float), stream>>>(p);
   else layernorm_bwd_kernel<false><<<grid, 256, 2 * C * sizeof(float), stream>>>(p);
+  note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -444,15 +445,15 @@ static int launch_window_gather(const void* in, void* out, int B, int H, int W, 
     const int CV = static_cast<int>(row_bytes / 16);
     const long total = static_cast<long>(B) * H * W * CV;
     window_gather_kernel<uint4><<<grid_for(total, 256), 256, 0, stream>>>(
-        static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, CV, shift, ws, scatter);
+        static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, CV, shift, ws, scatter); note_launch();
   } else if (elem_size == 4) {
     const long total = static_cast<long>(B) * H * W * C;
     window_gather_kernel<uint32_t><<<grid_for(total, 256), 256, 0, stream>>>(
-        static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), B, H, W, C, shift, ws, scatter);
+        static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), B, H, W, C, shift, ws, scatter); note_launch();
   } else {
     const long total = static_cast<long>(B) * H * W * C;
     window_gather_kernel<uint16_t><<<grid_for(total, 256), 256, 0, stream>>>(
-        static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), B, H, W, C, shift, ws, scatter);
+        static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), B, H, W, C, shift, ws, scatter); note_launch();
   }
   MTL_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -474,7 +475,7 @@ int launch_dropout(const void* x, void* y, long n, float p, uint64_t seed, cudaS
   MTL_REQUIRE(p >= 0.f && p < 1.f, "dropout probability has to be in [0, 1), but got %f", p);
   if (n == 0) return 0;
   dropout_kernel<<<grid_for(n / 8, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x),
-                                                          static_cast<__nv_bfloat16*>(y), n / 8, p, seed);
+                                                          static_cast<__nv_bfloat16*>(y), n / 8, p, seed); note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -486,7 +487,7 @@ int launch_scale_rows(const void* x, const float* scale, void* y, int S, long M,
   if (total == 0) return 0;
   scale_rows_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), scale,
                                                              static_cast<__nv_bfloat16*>(y), S, M, C / 8,
-                                                             rows_per_sample, static_cast<int>(M / rows_per_sample));
+                                                             rows_per_sample, static_cast<int>(M / rows_per_sample)); note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -496,7 +497,7 @@ int launch_add(const void* a, const void* b, void* out, long n, cudaStream_t str
   if (n == 0) return 0;
   add_kernel<<<grid_for(n / 8, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(a),
                                                       static_cast<const __nv_bfloat16*>(b),
-                                                      static_cast<__nv_bfloat16*>(out), n / 8);
+                                                      static_cast<__nv_bfloat16*>(out), n / 8); note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -506,7 +507,7 @@ int launch_sum_streams(const void* x, const void* extra, void* out, int S, long 
   if (n == 0) return 0;
   sum_streams_kernel<<<grid_for(n / 8, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x),
                                                               static_cast<const __nv_bfloat16*>(extra),
-                                                              static_cast<__nv_bfloat16*>(out), S, n / 8);
+                                                              static_cast<__nv_bfloat16*>(out), S, n / 8); note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -529,7 +530,7 @@ int launch_pack_adapters(const float* const* a_ptrs, const float* const* b_ptrs,
   p.a_cat_t = static_cast<__nv_bfloat16*>(a_cat_t);
   p.b_cat_t = static_cast<__nv_bfloat16*>(b_cat_t);
   const long total = static_cast<long>(R_pad) * (K + N);
-  pack_adapters_kernel<<<grid_for(total, 256), 256, 0, stream>>>(p);
+  pack_adapters_kernel<<<grid_for(total, 256), 256, 0, stream>>>(p); note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -538,7 +539,7 @@ int launch_cast_transpose(const float* w, void* w_bf16, void* wt_bf16, int rows,
   MTL_REQUIRE(rows > 0 && cols > 0, "cast_transpose: empty matrix");
   dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
   cast_transpose_kernel<<<grid, block, 0, stream>>>(w, static_cast<__nv_bfloat16*>(w_bf16),
-                                                   static_cast<__nv_bfloat16*>(wt_bf16), rows, cols);
+                                                   static_cast<__nv_bfloat16*>(wt_bf16), rows, cols); note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -137,7 +137,7 @@ int launch_xty(const void* P, long ldp, const void* Q, long ldq, float* C, long 
   mpc = (mpc + TM - 1) / TM * TM;
   p.m_per_cta = mpc;
   const unsigned gz = static_cast<unsigned>((M + mpc - 1) / mpc);
-  xty_kernel<<<dim3(at, bt, gz), 128, 0, stream>>>(p);
+  xty_kernel<<<dim3(at, bt, gz), 128, 0, stream>>>(p); note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

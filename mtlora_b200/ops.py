@@ -131,7 +131,8 @@ def linear_fwd(spec, x, w_bf16, bias, a_cat, b_cat, *, x_tasks_given=False, act_
     c = spec.cfg(M, x_tasks_given, dropout_p, seed, rows_per_sample)
     N.call("mtl_linear_fwd", ctypes.byref(c), N.ptr(x), N.ptr(w_bf16), N.ptr(bias), N.ptr(a_cat), N.ptr(b_cat),
            N.MTL_ACT_GELU if act_gelu else N.MTL_ACT_NONE, N.ptr(y), N.ptr(y_act), N.ptr(residual), res_streams,
-           N.ptr(path_scale), N.ptr(u), N.stream())
+           N.ptr(path_scale), N.ptr(u), N.stream(),
+           meta=("fwd", M, spec.K, spec.Nf, 1 + (spec.T if (x_tasks_given and spec.r_shared > 0) else 0), spec.S_out, spec.R_pad, sum(spec.ranks), bias is not None))
     return y, y_act, u
 
 
@@ -147,7 +148,8 @@ def linear_bwd_input(spec, dy, wt_bf16, a_cat_t, b_cat_t, *, x_tasks_given=False
     g = torch.empty((M, spec.R_pad), dtype=BF16, device=dy.device) if (save_g and spec.r_shared > 0) else None
     c = spec.cfg(M, x_tasks_given, dropout_p, seed, rows_per_sample)
     N.call("mtl_linear_bwd_input", ctypes.byref(c), N.ptr(dy), N.ptr(wt_bf16), N.ptr(a_cat_t), N.ptr(b_cat_t),
-           N.ptr(dx), N.ptr(gelu_aux), N.ptr(path_scale), N.ptr(g), N.stream())
+           N.ptr(dx), N.ptr(gelu_aux), N.ptr(path_scale), N.ptr(g), N.stream(),
+           meta=("bwd_input", M, spec.K, spec.Nf, dx.shape[0], S, spec.R_pad, sum(spec.ranks), False))
     return dx, g
 
 
@@ -160,7 +162,8 @@ def linear_bwd_params(spec, x, dy, u_save, g_save, *, x_tasks_given=False, x_gel
     db = torch.zeros((spec.Nf, spec.R_pad), dtype=torch.float32, device=dy.device)
     c = spec.cfg(M, x_tasks_given, dropout_p, 0, rows_per_sample)
     N.call("mtl_linear_bwd_params", ctypes.byref(c), N.ptr(x), 1 if x_gelu else 0, N.ptr(dy), N.ptr(u_save),
-           N.ptr(g_save), N.ptr(path_scale), N.ptr(da), N.ptr(db), N.stream())
+           N.ptr(g_save), N.ptr(path_scale), N.ptr(da), N.ptr(db), N.stream(),
+           meta=("bwd_params", M, spec.K, spec.Nf, x.shape[0], dy.shape[0], spec.R_pad, sum(spec.ranks), False))
     return da, db
 
 
