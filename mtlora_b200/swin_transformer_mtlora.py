@@ -396,6 +396,12 @@ class _BlockFn(torch.autograd.Function):
         grads = {}
         # fc2 -> d(fc1 pre-activation), GELU' fused into the epilogue
         dg, g2 = e_fc2.backward(sv["sv_2"], dy, gelu_aux=sv["g"])
+        if dys[0] is None and S > 1 and e_fc2.spec.r_shared > 0:
+            # the shared output stream is unused downstream (last stage, reference quirk: its fc2.lora_shared_{A,B}
+            # receive no gradient at all) -> report None like autograd does, not zeros
+            fc2 = blk.mlp.fc2
+            g2.pop(fc2.lora_shared_A, None)
+            g2.pop(fc2.lora_shared_B, None)
         grads.update(g2)
         dh2, g1 = e_fc1.backward(sv["sv_1"], dg)
         grads.update(g1)
