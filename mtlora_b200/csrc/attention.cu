@@ -211,11 +211,7 @@ __global__ void __launch_bounds__(128) win_attn_fwd_kernel(const AttnParams p) {
         const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
         uint32_t o4[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float lo = dropout_hash(p.drop_seed, off + 2 * e) >= thr ? bf16lo_to_f32(w4[e]) * keep_scale : 0.f;
-          const float hi = dropout_hash(p.drop_seed, off + 2 * e + 1) >= thr ? bf16hi_to_f32(w4[e]) * keep_scale : 0.f;
-          o4[e] = pack_bf16x2(lo, hi);
-        }
+        for (int e = 0; e < 4; ++e) o4[e] = dropout_apply_pair(w4[e], p.drop_seed, off + 2 * e, thr, keep_scale);
         *reinterpret_cast<uint4*>(p.out_drop + off) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
       }
     }

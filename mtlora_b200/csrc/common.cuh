@@ -56,18 +56,38 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16lo_to_f32(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi_to_f32(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
-// Counter-based dropout mask shared by every kernel: element `idx` (flat index in the [M, C] matrix the
-// LoRA dropout of models/lora.py:258 is applied to) is kept iff hash(seed, idx) >= p * 2^32.
+// Counter-based dropout mask shared by every kernel. Elements are addressed by their flat index in the [M, C]
+// matrix the LoRA dropout of models/lora.py:258 is applied to; one 32-bit hash serves the PAIR of adjacent elements
+// (2k, 2k+1) with 16 random bits each: element idx is kept iff its 16 bits (as the top half of a 32-bit word) are
+// >= dropout_threshold(p). 32-bit mixing only (lowbias32 finaliser) — the mask costs ~5 integer ops per element.
+__host__ __device__ __forceinline__ uint32_t dropout_seed_mix(uint64_t seed) {
+  uint32_t s = static_cast<uint32_t>(seed) ^ (static_cast<uint32_t>(seed >> 32) * 0x9E3779B1u) ^ 0x632BE59Bu;
+  s ^= s >> 16; s *= 0x7FEB352Du; s ^= s >> 15; s *= 0x846CA68Bu; s ^= s >> 16;
+  return s;
+}
+__host__ __device__ __forceinline__ uint32_t dropout_pair_bits(uint64_t seed, uint64_t pair_idx) {
+  const uint32_t lo = static_cast<uint32_t>(pair_idx), hi = static_cast<uint32_t>(pair_idx >> 32);
+  uint32_t h = lo * 0x9E3779B1u + dropout_seed_mix(seed);
+  h ^= hi * 0x85EBCA77u;
+  h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+  return h;
+}
+// element-level view of the same mask
 __host__ __device__ __forceinline__ uint32_t dropout_hash(uint64_t seed, uint64_t idx) {
-  uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return static_cast<uint32_t>(z >> 16);
+  const uint32_t h = dropout_pair_bits(seed, idx >> 1);
+  return (idx & 1) ? (h & 0xffff0000u) : (h << 16);
 }
 __host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
   const double t = static_cast<double>(p) * 4294967296.0;
   return t >= 4294967295.0 ? 0xffffffffu : static_cast<uint32_t>(t);
+}
+// D() of the packed bf16x2 word holding elements (idx, idx + 1), idx even: kept values are scaled by keep_scale.
+__device__ __forceinline__ uint32_t dropout_apply_pair(uint32_t w, uint64_t seed, uint64_t idx_even, uint32_t thr,
+                                                       float keep_scale) {
+  const uint32_t h = dropout_pair_bits(seed, idx_even >> 1);
+  const float lo = (h << 16) >= thr ? bf16lo_to_f32(w) * keep_scale : 0.f;
+  const float hi = (h & 0xffff0000u) >= thr ? bf16hi_to_f32(w) * keep_scale : 0.f;
+  return pack_bf16x2(lo, hi);
 }
 
 // exact (erf) GELU, matching torch.nn.GELU() default (swin_transformer_mtlora.py:45 act_layer=nn.GELU)
@@ -107,15 +127,33 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must trap (surfacing as a CUDA error) instead of hanging the GPU.
+// try_wait with a suspend-time hint: the thread sleeps in hardware (no issue slots) for up to `ns` nanoseconds
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (surfacing as a CUDA error) instead of hanging the GPU. The timer is only
+// consulted every 4096 unsuccessful polls so that waiting warps do not compete with working warps for issue slots.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
-  while (!mbar_try_wait(bar, parity)) {
-    if (globaltimer_ns() - t0 > 4000000000ull) {  // 4 s
-      printf("mtlora_b200: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n",
-             blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
+  uint32_t polls = 0;
+  uint64_t t0 = 0;
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if ((++polls & 4095u) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000ull) {  // 4 s
+        printf("mtlora_b200: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+               bar, parity);
+        __trap();
+      }
     }
   }
 }

@@ -1,40 +1,49 @@
-// Fused MTLoRALinear GEMM for sm_100a: frozen dense product + (1+T) low-rank adapters in one kernel.
+// Fused MTLoRALinear GEMM for sm_100a: frozen dense product + (1+T) low-rank adapters in one persistent kernel.
 //
-// Reference semantics: models/lora.py:253-284 (MTLoRALinear.forward) — the reference evaluates
-//   F.linear(x, W, b), 2(1+T) skinny matmuls and (1+T) mul/add passes as separate kernels.
-// Here each 128-row tile of X is staged by TMA, the rank-space products U = X.A_cat^T are formed by
-// tcgen05.mma into TMEM, re-staged as a bf16 K-major operand, and replayed against B_cat so that
-// every output stream is written exactly once; the frozen W tile is read once per tile and feeds all
-// streams (one dense accumulator P shared by the stream epilogues).
+// Reference semantics: models/lora.py:253-284 (MTLoRALinear.forward) — the reference evaluates F.linear(x, W, b),
+// 2(1+T) skinny matmuls and (1+T) mul/add passes as separate kernels. Here (see linear_sm100.cuh for the algebra):
+//   * one persistent CTA per SM walks the (128-row tile, column split) work list;
+//   * TMA stages X / W / A_cat / B_cat tiles in a shared-memory ring, tcgen05.mma accumulates in TMEM;
+//   * the rank-space activations U = X.A_cat^T are formed once per tile, converted to a bf16 K-major operand in
+//     shared memory and replayed against B_cat for every output stream ("stream-sequential" delta accumulators);
+//   * the dense accumulator P of a column chunk is shared by all (1+T) stream epilogues;
+//   * two epilogue warp-groups (4 warps each = the 4 TMEM lane quadrants) ping-pong over the items
+//     (chunk, stream): TMEM -> registers -> bias / DropPath scale / GELU / residual -> bf16 -> swizzled smem slab ->
+//     TMA store, so every output element is written exactly once by coalesced bulk stores.
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4-7 = U converter + epilogue (each owns 32 TMEM lanes = 32 tile rows).
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-7 = epilogue group 0, warps 8-11 = epilogue group 1 (warp % 4 = TMEM lane quadrant).
 #include "linear_sm100.cuh"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 #include <mutex>
 
 namespace mtl {
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kStageABytes = LIN_BM * LIN_BK * 2;  // 16 KiB
+constexpr int kThreads = 384;
+constexpr int kEpiThreads = 256;
+constexpr int kTileABytes = LIN_BM * LIN_BK * 2;  // 16 KiB: one [128 x 64] bf16 K-major SW128 tile
+constexpr int kSlabBytes = 32 * 64 * 2;           // 4 KiB: one warp's [32 rows x 64 cols] bf16 store slab
+constexpr int kMaxStages = 8;
+constexpr int kMaxUAtoms = LIN_MAX_GRAN / 4;
 
 struct SmemLayout {
-  uint32_t stages;   // n_stages * (A + B)
-  uint32_t usm;      // n_uatoms * 16 KiB
-  uint32_t bars;     // mbarriers
+  uint32_t usm;    // n_uatoms * 16 KiB
+  uint32_t slabs;  // 8 warps * n_slabs * 4 KiB
+  uint32_t bars;
   uint32_t total;
 };
 
-__host__ __device__ inline SmemLayout smem_layout(int n_stages, int stage_b_bytes, int r_pad) {
+__host__ __device__ inline SmemLayout smem_layout(int n_stages, int stage_bytes, int r_pad, int n_slabs) {
   SmemLayout l;
   const uint32_t n_uatoms = (r_pad + 63) / 64;
-  l.stages = 0;
-  l.usm = n_stages * (kStageABytes + stage_b_bytes);
-  l.bars = l.usm + n_uatoms * kStageABytes;
-  l.total = l.bars + 256;
+  l.usm = n_stages * stage_bytes;
+  l.slabs = l.usm + n_uatoms * kTileABytes;
+  l.bars = l.slabs + 8 * n_slabs * kSlabBytes;
+  l.total = l.bars + 512;
   return l;
 }
 
@@ -43,41 +52,131 @@ __device__ __forceinline__ bool col_in_out(const LinPlan& p, int j, int col) {
          (col >= p.out_r0[j][1] && col < p.out_r0[j][1] + p.out_len[j][1]);
 }
 
-__global__ void __launch_bounds__(kThreads)
+// ---- TMA stores (shared -> global), bulk-group completion ------------------------------------------------------
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kEpiThreads) : "memory");
+}
+
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 on sm_100) -----------------------------------------------------------
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+#define MTL_C2(c) pack2(c, c)
+
+// Branch-free normal CDF for the GELU epilogues: Phi(x) = 0.5 + x * Q(x^2), Q an odd-minimax fit of
+// 0.5 * erf(x / sqrt 2) on |x| <= 4.25 (max abs error 1.1e-5, far below the bf16 resolution of the outputs); the
+// argument is clamped, so Phi saturates at 1 - 1e-5 / 1e-5. nn.GELU() is the exact-erf GELU (reference :45):
+// GELU(x) = x * Phi(x), GELU'(x) = Phi(x) + x * phi(x). Two elements per instruction.
+__device__ __forceinline__ uint64_t phi2(float x0, float x1) {
+  const uint64_t xc = pack2(fminf(fmaxf(x0, -4.25f), 4.25f), fminf(fmaxf(x1, -4.25f), 4.25f));
+  const uint64_t t = mul2(xc, xc);
+  uint64_t q = MTL_C2(5.565109802e-11f);
+  q = fma2(q, t, MTL_C2(-5.327931323e-09f));
+  q = fma2(q, t, MTL_C2(2.255476184e-07f));
+  q = fma2(q, t, MTL_C2(-5.626496851e-06f));
+  q = fma2(q, t, MTL_C2(9.341922331e-05f));
+  q = fma2(q, t, MTL_C2(-1.108562514e-03f));
+  q = fma2(q, t, MTL_C2(9.815966060e-03f));
+  q = fma2(q, t, MTL_C2(-6.634444852e-02f));
+  q = fma2(q, t, MTL_C2(3.989024332e-01f));
+  return fma2(xc, q, MTL_C2(0.5f));
+}
+__device__ __forceinline__ void gelu_fast2(float x0, float x1, float& g0, float& g1) {
+  unpack2(mul2(pack2(x0, x1), phi2(x0, x1)), g0, g1);
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void gelu_grad_fast2(float x0, float x1, float& d0, float& d1) {
+  // pdf = exp(-x^2 / 2) / sqrt(2 pi)
+  const float p0 = 0.39894228040143267794f * ex2_approx(-0.72134752044448170368f * x0 * x0);
+  const float p1 = 0.39894228040143267794f * ex2_approx(-0.72134752044448170368f * x1 * x1);
+  unpack2(fma2(pack2(x0, x1), pack2(p0, p1), phi2(x0, x1)), d0, d1);
+}
+
+struct WorkItem {
+  int m0, split, n_my_chunks;
+};
+__device__ __forceinline__ WorkItem get_work(const LinPlan& p, int w) {
+  WorkItem it;
+  const int m_tile = w / p.n_splits;
+  it.split = w - m_tile * p.n_splits;
+  it.m0 = m_tile * LIN_BM;
+  it.n_my_chunks = (p.n_chunks - it.split + p.n_splits - 1) / p.n_splits;
+  return it;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
 mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                  const __grid_constant__ CUtensorMap tm_down,
-                  const __grid_constant__ CUtensorMap tm_up, const __grid_constant__ LinPlan p) {
+                  const __grid_constant__ CUtensorMap tm_down, const __grid_constant__ CUtensorMap tm_up,
+                  const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_y2,
+                  const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ LinPlan p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
-  const SmemLayout L = smem_layout(p.n_stages, p.stage_b_bytes, p.R_pad);
-  const uint32_t stage_bytes = kStageABytes + p.stage_b_bytes;
+  const uint32_t stage_bytes = kTileABytes + p.stage_b_bytes;
+  const SmemLayout L = smem_layout(p.n_stages, stage_bytes, p.R_pad, p.n_slabs);
   const uint32_t usm_base = smem_base + L.usm;
   const uint32_t bar_base = smem_base + L.bars;
-  // barrier slots (8 bytes each)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
   const uint32_t u_full = bar_base + 8u * 16;
   const uint32_t u_ready = bar_base + 8u * 17;
-  auto acc_full = [&](int b) { return bar_base + 8u * (18 + b); };
-  auto acc_empty = [&](int b) { return bar_base + 8u * (20 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * 22;
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L.bars + 8u * 22);
+  const uint32_t usm_free = bar_base + 8u * 18;
+  auto p_full = [&](int b) { return bar_base + 8u * (20 + b); };
+  auto p_empty = [&](int b) { return bar_base + 8u * (22 + b); };
+  auto d_full = [&](int b) { return bar_base + 8u * (24 + b); };    // b = group * 2 + buffer
+  auto d_empty = [&](int b) { return bar_base + 8u * (28 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * 32;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L.bars + 8u * 32);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  const int m_tile = blockIdx.x / p.n_splits;
-  const int split = blockIdx.x % p.n_splits;
-  const int m0 = m_tile * LIN_BM;
   const int n_kb = (p.Kc + LIN_BK - 1) / LIN_BK;
   const int n_uatoms = (p.R_pad + 63) / 64;
-  const int n_my_chunks = (p.n_chunks - split + p.n_splits - 1) / p.n_splits;
+  const bool multi = p.n_regions > 1;
+  const int n_work = p.n_work;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_y);
     if (p.R_pad > 0) {
       tma_prefetch_desc(&tm_down);
       tma_prefetch_desc(&tm_up);
@@ -87,10 +186,15 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(u_full, 1);
-    mbar_init(u_ready, 128);
+    mbar_init(u_ready, kEpiThreads);
+    mbar_init(usm_free, 1);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(acc_full(b), 1);
-      mbar_init(acc_empty(b), 128);
+      mbar_init(p_full(b), 1);
+      mbar_init(p_empty(b), kEpiThreads);
+    }
+    for (int b = 0; b < 4; ++b) {
+      mbar_init(d_full(b), 1);
+      mbar_init(d_empty(b), kEpiThreads / 2);
     }
     mbar_fence_init();
   }
@@ -102,9 +206,13 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  // TMEM columns: [0, u_cols) rank-space accumulators U; then P[n_pbuf] (multi); then D[group][n_dbuf]
+  // item G -> group G & 1, that group's k-th item (k = G >> 1) -> buffer k % n_dbuf, use k / n_dbuf
+  const uint32_t p_col0 = p.acc_col0;
+  const uint32_t d_col0 = p.acc_col0 + (multi ? p.n_pbuf * p.BN : 0);
 
   if (warp == 0) {
-    // ===================================== TMA producer =====================================
+    // ============================================ TMA producer ============================================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -114,46 +222,49 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           phase ^= 1u;
         }
       };
-      // phase 1: rank-space ("down") products
-      for (int g = 0; g < p.n_groups; ++g) {
-        const int len = p.grp_len[g];
-        for (int kb = 0; kb < n_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t a_dst = smem_base + stage * stage_bytes;
-          const uint32_t b_dst = a_dst + kStageABytes;
-          mbar_arrive_expect_tx(full_bar(stage), kStageABytes + len * 128);
-          tma_load_3d(a_dst, &tm_x, full_bar(stage), kb * LIN_BK, m0, p.grp_in[g]);
-          for (int i = 0; i < len / 16; ++i)
-            tma_load_2d(b_dst + i * 2048, &tm_down, full_bar(stage), kb * LIN_BK, p.grp_r0[g] + 16 * i);
-          advance();
-        }
-      }
-      // phase 2: dense product + adapter replay per output chunk
-      for (int ci = 0; ci < n_my_chunks; ++ci) {
-        const int c = split + ci * p.n_splits;
-        for (int i = 0; i < p.n_main; ++i) {
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const WorkItem it = get_work(p, w);
+        // phase 1: rank-space ("down") products
+        for (int g = 0; g < p.n_groups; ++g) {
+          const int len = p.grp_len[g];
           for (int kb = 0; kb < n_kb; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t a_dst = smem_base + stage * stage_bytes;
-            const uint32_t b_dst = a_dst + kStageABytes;
-            mbar_arrive_expect_tx(full_bar(stage), kStageABytes + p.BN * 128);
-            tma_load_3d(a_dst, &tm_x, full_bar(stage), kb * LIN_BK, m0, p.main_in[i]);
-            tma_load_2d(b_dst, &tm_w, full_bar(stage), kb * LIN_BK, c * p.BN);
+            const uint32_t b_dst = a_dst + kTileABytes;
+            mbar_arrive_expect_tx(full_bar(stage), kTileABytes + len * 128);
+            tma_load_3d(a_dst, &tm_x, full_bar(stage), kb * LIN_BK, it.m0, p.grp_in[g]);
+            for (int i = 0; i < len / 16; ++i)
+              tma_load_2d(b_dst + i * 2048, &tm_down, full_bar(stage), kb * LIN_BK, p.grp_r0[g] + 16 * i);
             advance();
           }
         }
-        for (int a = 0; a < n_uatoms; ++a) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t b_dst = smem_base + stage * stage_bytes + kStageABytes;
-          mbar_arrive_expect_tx(full_bar(stage), p.BN * 128);
-          tma_load_2d(b_dst, &tm_up, full_bar(stage), a * 64, c * p.BN);
-          advance();
+        // phase 2: dense product + adapter replay per output chunk
+        for (int ci = 0; ci < it.n_my_chunks; ++ci) {
+          const int c = it.split + ci * p.n_splits;
+          for (int i = 0; i < p.n_main; ++i) {
+            for (int kb = 0; kb < n_kb; ++kb) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              const uint32_t a_dst = smem_base + stage * stage_bytes;
+              const uint32_t b_dst = a_dst + kTileABytes;
+              mbar_arrive_expect_tx(full_bar(stage), kTileABytes + p.BN * 128);
+              tma_load_3d(a_dst, &tm_x, full_bar(stage), kb * LIN_BK, it.m0, p.main_in[i]);
+              tma_load_2d(b_dst, &tm_w, full_bar(stage), kb * LIN_BK, c * p.BN);
+              advance();
+            }
+          }
+          for (int a = 0; a < n_uatoms; ++a) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t b_dst = smem_base + stage * stage_bytes + kTileABytes;
+            mbar_arrive_expect_tx(full_bar(stage), p.BN * 128);
+            tma_load_2d(b_dst, &tm_up, full_bar(stage), a * 64, c * p.BN);
+            advance();
+          }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ====================================== MMA issuer ======================================
+    // ============================================= MMA issuer =============================================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -163,242 +274,361 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           phase ^= 1u;
         }
       };
-      for (int g = 0; g < p.n_groups; ++g) {
-        const uint32_t idesc = umma_idesc_bf16_m128(p.grp_len[g]);
-        const uint32_t d_tmem = tmem_base + p.grp_r0[g];
-        for (int kb = 0; kb < n_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t a_src = smem_base + stage * stage_bytes;
-          const uint64_t adesc = umma_desc_sw128(a_src);
-          const uint64_t bdesc = umma_desc_sw128(a_src + kStageABytes);
-          for (int q = 0; q < 4; ++q) {
-            if (kb * LIN_BK + q * 16 >= p.Kc) break;
-            umma_bf16(d_tmem, adesc + 2 * q, bdesc + 2 * q, idesc, ((kb | q) != 0 || p.grp_acc[g]) ? 1u : 0u);
-          }
-          umma_commit(empty_bar(stage));
-          advance();
-        }
-      }
-      if (p.R_pad > 0) umma_commit(u_full);
-
-      const uint32_t idesc_bn = umma_idesc_bf16_m128(p.BN);
-      bool u_waited = false;
-      for (int ci = 0; ci < n_my_chunks; ++ci) {
-        const int b = ci % p.n_acc;
-        const uint32_t use = ci / p.n_acc;
-        mbar_wait(acc_empty(b), (use & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t acc0 = tmem_base + p.acc_col0 + b * p.n_regions * p.BN;
-        bool first = true;
-        for (int i = 0; i < p.n_main; ++i) {
+      uint32_t lw = 0, Cn = 0, G = 0;  // local work / chunk / item counters (same sequence in the epilogue warps)
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++lw) {
+        const WorkItem it = get_work(p, w);
+        // ---- phase 1: U[:, group] = X[in] . Down[group]^T (the U columns were drained before u_ready of the
+        //      previous work item, which this thread has already waited for)
+        for (int g = 0; g < p.n_groups; ++g) {
+          const uint32_t idesc = umma_idesc_bf16_m128(p.grp_len[g]);
+          const uint32_t d_tmem = tmem_base + p.grp_r0[g];
           for (int kb = 0; kb < n_kb; ++kb) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
             const uint32_t a_src = smem_base + stage * stage_bytes;
             const uint64_t adesc = umma_desc_sw128(a_src);
-            const uint64_t bdesc = umma_desc_sw128(a_src + kStageABytes);
+            const uint64_t bdesc = umma_desc_sw128(a_src + kTileABytes);
             for (int q = 0; q < 4; ++q) {
               if (kb * LIN_BK + q * 16 >= p.Kc) break;
-              umma_bf16(acc0, adesc + 2 * q, bdesc + 2 * q, idesc_bn, first ? 0u : 1u);
-              first = false;
+              umma_bf16(d_tmem, adesc + 2 * q, bdesc + 2 * q, idesc, ((kb | q) != 0 || p.grp_acc[g]) ? 1u : 0u);
             }
             umma_commit(empty_bar(stage));
             advance();
           }
         }
-        uint32_t region_started = 0;  // bit r: region r already holds a partial sum
-        if (!first) region_started |= 1u;
-        for (int a = 0; a < n_uatoms; ++a) {
-          if (!u_waited) {
-            mbar_wait(u_ready, 0);
-            u_waited = true;
+        if (p.R_pad > 0) umma_commit(u_full);
+        bool u_waited = (p.R_pad == 0);
+
+        for (int ci = 0; ci < it.n_my_chunks; ++ci) {
+          const int c = it.split + ci * p.n_splits;
+          int n_eff = p.Nn - c * p.BN;
+          if (n_eff > p.BN) n_eff = p.BN;
+          const uint32_t idesc_bn = umma_idesc_bf16_m128(n_eff);
+          uint32_t acc_dense;  // where the dense product accumulates
+          uint32_t g0 = 0;
+          if (multi) {
+            const uint32_t pb = Cn % p.n_pbuf;
+            mbar_wait(p_empty(pb), ((Cn / p.n_pbuf) & 1u) ^ 1u);
+            acc_dense = tmem_base + p_col0 + pb * p.BN;
+          } else {
+            const uint32_t k = G >> 1;
+            g0 = (G & 1u) * 2 + k % p.n_dbuf;
+            mbar_wait(d_empty(g0), ((k / p.n_dbuf) & 1u) ^ 1u);
+            acc_dense = tmem_base + d_col0 + ((G & 1u) * p.n_dbuf + k % p.n_dbuf) * p.BN;
           }
-          mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint64_t adesc = umma_desc_sw128(usm_base + a * kStageABytes);
-          const uint64_t bdesc = umma_desc_sw128(smem_base + stage * stage_bytes + kStageABytes);
-          for (int q = 0; q < 4; ++q) {
-            const int col = a * 64 + q * 16;
-            if (col >= p.R_pad) break;
-            for (int j = 0; j < p.S_out; ++j) {
-              if (!col_in_out(p, j, col)) continue;
-              const int region = (p.n_regions == 1) ? 0 : 1 + j;
-              umma_bf16(acc0 + region * p.BN, adesc + 2 * q, bdesc + 2 * q, idesc_bn,
-                        (region_started >> region) & 1u);
-              region_started |= 1u << region;
+          bool first = true;
+          for (int i = 0; i < p.n_main; ++i) {
+            for (int kb = 0; kb < n_kb; ++kb) {
+              mbar_wait(full_bar(stage), phase);
+              tc_fence_after();
+              const uint32_t a_src = smem_base + stage * stage_bytes;
+              const uint64_t adesc = umma_desc_sw128(a_src);
+              const uint64_t bdesc = umma_desc_sw128(a_src + kTileABytes);
+              for (int q = 0; q < 4; ++q) {
+                if (kb * LIN_BK + q * 16 >= p.Kc) break;
+                umma_bf16(acc_dense, adesc + 2 * q, bdesc + 2 * q, idesc_bn, first ? 0u : 1u);
+                first = false;
+              }
+              umma_commit(empty_bar(stage));
+              advance();
             }
           }
-          umma_commit(empty_bar(stage));
-          advance();
+          if (multi) umma_commit(p_full(Cn % p.n_pbuf));
+          if (n_uatoms > 0) {
+            if (!u_waited) {
+              mbar_wait(u_ready, lw & 1u);
+              u_waited = true;
+            }
+            // the B_cat tiles of all rank atoms of this chunk occupy n_uatoms consecutive ring stages
+            int st[kMaxUAtoms];
+            {
+              int s = stage;
+              uint32_t ph = phase;
+              for (int a = 0; a < n_uatoms; ++a) {
+                mbar_wait(full_bar(s), ph);
+                st[a] = s;
+                if (++s == p.n_stages) {
+                  s = 0;
+                  ph ^= 1u;
+                }
+              }
+            }
+            tc_fence_after();
+            const int n_items = multi ? p.S_out : 1;
+            for (int j = 0; j < n_items; ++j) {
+              uint32_t acc;
+              bool started;
+              uint32_t db = 0;
+              if (multi) {
+                const uint32_t k = G >> 1;
+                db = (G & 1u) * 2 + k % p.n_dbuf;
+                mbar_wait(d_empty(db), ((k / p.n_dbuf) & 1u) ^ 1u);
+                tc_fence_after();
+                acc = tmem_base + d_col0 + ((G & 1u) * p.n_dbuf + k % p.n_dbuf) * p.BN;
+                started = false;
+              } else {
+                acc = acc_dense;
+                started = !first;
+              }
+              for (int a = 0; a < n_uatoms; ++a) {
+                const uint64_t adesc = umma_desc_sw128(usm_base + a * kTileABytes);
+                const uint64_t bdesc = umma_desc_sw128(smem_base + st[a] * stage_bytes + kTileABytes);
+                for (int q = 0; q < 4; ++q) {
+                  const int col = a * 64 + q * 16;
+                  if (col >= p.R_pad) break;
+                  if (!col_in_out(p, j, col)) continue;
+                  umma_bf16(acc, adesc + 2 * q, bdesc + 2 * q, idesc_bn, started ? 1u : 0u);
+                  started = true;
+                }
+              }
+              if (multi) {
+                umma_commit(d_full(db));
+                ++G;
+              }
+            }
+            for (int a = 0; a < n_uatoms; ++a) {
+              umma_commit(empty_bar(stage));
+              advance();
+            }
+          }
+          if (multi) {
+            ++Cn;
+          } else {
+            umma_commit(d_full(g0));
+            ++G;
+          }
         }
-        umma_commit(acc_full(b));
+        if (p.R_pad > 0) umma_commit(usm_free);
       }
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // =============================== U converter + epilogue ================================
-    const int w = warp - 4;
-    const int row = w * 32 + lane;
-    const int grow = m0 + row;
-    const bool row_ok = grow < p.M;
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(w * 32) << 16);
-    const int sample = (p.rows_per_sample > 0) ? min(grow / p.rows_per_sample, p.n_samples - 1) : 0;
-
-    if (p.R_pad > 0) {
-      mbar_wait(u_full, 0);
-      tc_fence_after();
-      for (int gq = 0; gq < p.R_pad / 16; ++gq) {
-        uint32_t r[16];
-        tmem_ld16(t_lane + gq * 16, r);
-        tmem_ld_wait();
-        float s = p.gran_scale[gq];
-        if (p.rowscale_in != nullptr) s *= p.rowscale_in[p.gran_in[gq] * p.n_samples + sample];
-        uint32_t pk[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          pk[i] = pack_bf16x2(__uint_as_float(r[2 * i]) * s, __uint_as_float(r[2 * i + 1]) * s);
-        uint8_t* atom = smem_gen + L.usm + (gq >> 2) * kStageABytes;
-        const uint32_t c0 = (gq & 3) * 16;
-        *reinterpret_cast<uint4*>(atom + sw128_offset(row, c0)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(atom + sw128_offset(row, c0 + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        if (p.u_save != nullptr && split == 0 && row_ok) {
-          uint4* dst = reinterpret_cast<uint4*>(p.u_save + static_cast<size_t>(grow) * p.R_pad + gq * 16);
-          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(u_ready);
-    }
-
+    // ======================================= U converter + epilogue =======================================
+    const int q4 = warp & 3;                 // TMEM lane quadrant
+    const uint32_t grp = (warp - 4) >> 2;    // epilogue group 0 / 1
+    const int ew = warp - 4;                 // 0..7
+    const int row = q4 * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
+    uint8_t* slab_gen = smem_gen + L.slabs + ew * p.n_slabs * kSlabBytes;
+    const uint32_t slab_base = smem_base + L.slabs + ew * p.n_slabs * kSlabBytes;
+    int slab_k = 0;
+    const bool is_t0 = (warp == 4 && lane == 0);
+    const uint32_t thr = dropout_threshold(p.drop_p);
+    const float keep_scale = 1.f / (1.f - p.drop_p);
     const size_t stream_stride = static_cast<size_t>(p.M) * p.Nn;
-    for (int ci = 0; ci < n_my_chunks; ++ci) {
-      const int c = split + ci * p.n_splits;
-      const int b = ci % p.n_acc;
-      const uint32_t use = ci / p.n_acc;
-      mbar_wait(acc_full(b), use & 1u);
-      tc_fence_after();
-      const uint32_t acc0 = t_lane + p.acc_col0 + b * p.n_regions * p.BN;
-      for (int gq = 0; gq < p.BN / 16; ++gq) {
-        const int n0 = c * p.BN + gq * 16;
-        if (n0 >= p.Nn) break;
-        uint32_t pr[16];
-        bool have_p = false;
-        if (p.n_regions > 1 && p.n_main > 0) {
-          tmem_ld16(acc0 + gq * 16, pr);
-          have_p = true;
+    const bool dual = p.ep_mode == LIN_EP_GELU_DUAL;
+
+    uint32_t lw = 0, Cn = 0, G = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++lw) {
+      const WorkItem it = get_work(p, w);
+      const int grow = it.m0 + row;
+      const bool row_ok = grow < p.M;
+      const int sample = (p.rows_per_sample > 0) ? min(grow / p.rows_per_sample, p.n_samples - 1) : 0;
+      const int row0 = it.m0 + q4 * 32;
+
+      if (p.R_pad > 0) {
+        mbar_wait(u_full, lw & 1u);
+        tc_fence_after();
+        if (lw > 0) mbar_wait(usm_free, (lw - 1) & 1u);  // previous item's delta MMAs finished reading usm
+        if (p.u_save != nullptr) {
+          if (is_t0) bulk_wait_read<0>();                 // ... and so did its u_save bulk stores
+          epi_bar_sync(1);
         }
-        float bias_v[16];
-        if (p.bias != nullptr) {
+        for (int gq = static_cast<int>(grp); gq < p.R_pad / 16; gq += 2) {
+          uint32_t r[16];
+          tmem_ld16(t_lane + gq * 16, r);
+          tmem_ld_wait();
+          float s = p.gran_scale[gq];
+          if (p.rowscale_in != nullptr) s *= p.rowscale_in[p.gran_in[gq] * p.n_samples + sample];
+          uint32_t pk[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
-            bias_v[4 * i + 0] = bv.x; bias_v[4 * i + 1] = bv.y;
-            bias_v[4 * i + 2] = bv.z; bias_v[4 * i + 3] = bv.w;
+          for (int i = 0; i < 8; ++i)
+            pk[i] = pack_bf16x2(__uint_as_float(r[2 * i]) * s, __uint_as_float(r[2 * i + 1]) * s);
+          uint8_t* atom = smem_gen + L.usm + (gq >> 2) * kTileABytes;
+          const uint32_t c0 = (gq & 3) * 16;
+          *reinterpret_cast<uint4*>(atom + sw128_offset(row, c0)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(atom + sw128_offset(row, c0 + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        if (p.u_save != nullptr && it.split == 0) {
+          epi_bar_sync(2);
+          if (is_t0) {
+            for (int a = 0; a < n_uatoms; ++a) tma_store_2d(&tm_u, usm_base + a * kTileABytes, a * 64, it.m0);
+            bulk_commit();
           }
         }
-        for (int j = 0; j < p.S_out; ++j) {
-          float v[16];
-          const bool has_delta = (p.out_len[j][0] + p.out_len[j][1]) > 0;
-          if (p.n_regions == 1) {
-            uint32_t dr[16];
-            tmem_ld16(acc0 + gq * 16, dr);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(dr[i]);
-          } else {
-            uint32_t dr[16];
-            if (has_delta) tmem_ld16(acc0 + (1 + j) * p.BN + gq * 16, dr);
-            tmem_ld_wait();
-            const bool mask_delta = (p.drop_mode == 2) && j == 0;
-            const uint32_t thr = dropout_threshold(p.drop_p);
-            const float keep_scale = 1.f / (1.f - p.drop_p);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float t = 0.f;
-              if (have_p && p.out_useP[j]) t = __uint_as_float(pr[i]);
-              if (has_delta) {
-                float d = __uint_as_float(dr[i]);
-                if (mask_delta)
-                  d = dropout_hash(p.drop_seed, static_cast<uint64_t>(grow) * p.Nn + n0 + i) >= thr ? d * keep_scale : 0.f;
-                t += d;
-              }
-              v[i] = t;
-            }
+        mbar_arrive(u_ready);
+      }
+
+      for (int ci = 0; ci < it.n_my_chunks; ++ci) {
+        const int c = it.split + ci * p.n_splits;
+        int n_eff = p.Nn - c * p.BN;
+        if (n_eff > p.BN) n_eff = p.BN;
+        const int n_items = multi ? p.S_out : 1;
+        const uint32_t pb = multi ? (Cn % p.n_pbuf) : 0;
+        bool p_waited = false;
+        for (int j = 0; j < n_items; ++j, ++G) {
+          if ((G & 1u) != grp) continue;
+          const uint32_t kk = G >> 1, dbuf = kk % p.n_dbuf, db = grp * 2 + dbuf;
+          mbar_wait(d_full(db), (kk / p.n_dbuf) & 1u);
+          const bool use_p = multi && p.out_useP[j];
+          if (use_p && !p_waited) {
+            mbar_wait(p_full(pb), (Cn / p.n_pbuf) & 1u);
+            p_waited = true;
           }
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += bias_v[i];
-          }
-          if (p.rowscale_out != nullptr) {
-            const float rs = p.rowscale_out[j * p.n_samples + sample];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] *= rs;
-          }
-          if (row_ok) {
-            const size_t off = j * stream_stride + static_cast<size_t>(grow) * p.Nn + n0;
-            if (p.ep_mode == LIN_EP_GELU_BWD) {
-              const uint4* ap = reinterpret_cast<const uint4*>(p.aux + off);
-              const uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
-              const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                v[2 * i] *= gelu_exact_grad(bf16lo_to_f32(aw[i]));
-                v[2 * i + 1] *= gelu_exact_grad(bf16hi_to_f32(aw[i]));
-              }
-            }
-            if (p.res != nullptr) {
-              const size_t roff = (p.res_streams == 1 ? 0 : j * stream_stride) +
-                                  static_cast<size_t>(grow) * p.Nn + n0;
-              const uint4* rp = reinterpret_cast<const uint4*>(p.res + roff);
-              const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                v[2 * i] += bf16lo_to_f32(rw[i]);
-                v[2 * i + 1] += bf16hi_to_f32(rw[i]);
-              }
-            }
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-            uint4* dst = reinterpret_cast<uint4*>(p.y + off);
-            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            if (p.ep_mode == LIN_EP_GELU_DUAL) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                pk[i] = pack_bf16x2(gelu_exact(v[2 * i]), gelu_exact(v[2 * i + 1]));
-              uint4* dst2 = reinterpret_cast<uint4*>(p.y2 + off);
-              dst2[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              dst2[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-              if (p.drop_mode == 1 && j == 0) {
-                // D(m): derived from the bf16-rounded activation so it equals dropout(y2, seed + 1) exactly; the next
-                // layer (fc2) is called with dropout_seed + 1 so that its mask is independent of this layer's input mask
-                const uint32_t thr = dropout_threshold(p.drop_p);
-                const float keep_scale = 1.f / (1.f - p.drop_p);
-                const uint64_t e0 = static_cast<uint64_t>(grow) * p.Nn + n0;
+          tc_fence_after();
+          const uint32_t acc_d = t_lane + d_col0 + (grp * p.n_dbuf + dbuf) * p.BN;
+          const uint32_t acc_p = t_lane + p_col0 + pb * p.BN;
+          const bool mask_delta = multi && (p.drop_mode == 2) && j == 0;
+          const float rs = (p.rowscale_out != nullptr) ? p.rowscale_out[j * p.n_samples + sample] : 1.f;
+          const int n_half = (n_eff + 63) >> 6;
+          for (int h = 0; h < n_half; ++h) {
+            const int col_h = c * p.BN + h * 64;
+            // slabs of this half: y -> ks_y, GELU(y) -> ks_y2. A slab is reused every n_slabs stores; with at most
+            // n_slabs - n_out bulk groups still pending the ones that used these slabs have been read.
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+            const int n_out = dual ? 2 : 1;
+            const int ks_y = slab_k;
+            const int ks_y2 = (slab_k + 1) % p.n_slabs;
+            uint8_t* sy = slab_gen + ks_y * kSlabBytes;
+            uint8_t* sy2 = slab_gen + ks_y2 * kSlabBytes;
+#pragma unroll 1
+            for (int gq = 0; gq < 4; ++gq) {
+              const int n0 = col_h + gq * 16;
+              if (n0 >= p.Nn) break;
+              const int tcol = h * 64 + gq * 16;
+              uint32_t pr[16], dr[16];
+              if (use_p) tmem_ld16(acc_p + tcol, pr);
+              tmem_ld16(acc_d + tcol, dr);
+              tmem_ld_wait();
+              float v[16];
+              if (mask_delta) {
+                const uint64_t e0 = (static_cast<uint64_t>(grow) * p.Nn + n0) >> 1;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                  const float lo = dropout_hash(p.drop_seed + 1, e0 + 2 * i) >= thr ? bf16lo_to_f32(pk[i]) * keep_scale : 0.f;
-                  const float hi = dropout_hash(p.drop_seed + 1, e0 + 2 * i + 1) >= thr ? bf16hi_to_f32(pk[i]) * keep_scale : 0.f;
-                  pk[i] = pack_bf16x2(lo, hi);
+                  const uint32_t hsh = dropout_pair_bits(p.drop_seed, e0 + i);
+                  dr[2 * i] = (hsh << 16) >= thr ? __float_as_uint(__uint_as_float(dr[2 * i]) * keep_scale) : 0u;
+                  dr[2 * i + 1] =
+                      (hsh & 0xffff0000u) >= thr ? __float_as_uint(__uint_as_float(dr[2 * i + 1]) * keep_scale) : 0u;
                 }
-                uint4* dst3 = reinterpret_cast<uint4*>(p.y2 + static_cast<size_t>(p.S_out) * stream_stride +
-                                                       static_cast<size_t>(grow) * p.Nn + n0);
-                dst3[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                dst3[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                v[i] = use_p ? __uint_as_float(dr[i]) + __uint_as_float(pr[i]) : __uint_as_float(dr[i]);
+              if (p.bias != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
+                  v[4 * i + 0] += bv.x; v[4 * i + 1] += bv.y; v[4 * i + 2] += bv.z; v[4 * i + 3] += bv.w;
+                }
+              }
+              if (p.rowscale_out != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] *= rs;
+              }
+              if (row_ok) {
+                const size_t off = j * stream_stride + static_cast<size_t>(grow) * p.Nn + n0;
+                if (p.ep_mode == LIN_EP_GELU_BWD) {
+                  const uint4* ap = reinterpret_cast<const uint4*>(p.aux + off);
+                  const uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
+                  const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    float d0, d1;
+                    gelu_grad_fast2(bf16lo_to_f32(aw[i]), bf16hi_to_f32(aw[i]), d0, d1);
+                    v[2 * i] *= d0;
+                    v[2 * i + 1] *= d1;
+                  }
+                }
+                if (p.res != nullptr) {
+                  const size_t roff =
+                      (p.res_streams == 1 ? 0 : j * stream_stride) + static_cast<size_t>(grow) * p.Nn + n0;
+                  const uint4* rp = reinterpret_cast<const uint4*>(p.res + roff);
+                  const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                  const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    v[2 * i] += bf16lo_to_f32(rw[i]);
+                    v[2 * i + 1] += bf16hi_to_f32(rw[i]);
+                  }
+                }
+              }
+              uint32_t pk[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+              *reinterpret_cast<uint4*>(sy + sw128_offset(lane, gq * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(sy + sw128_offset(lane, gq * 16 + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              if (dual) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  float g0v, g1v;
+                  gelu_fast2(v[2 * i], v[2 * i + 1], g0v, g1v);
+                  pk[i] = pack_bf16x2(g0v, g1v);
+                }
+                *reinterpret_cast<uint4*>(sy2 + sw128_offset(lane, gq * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(sy2 + sw128_offset(lane, gq * 16 + 8)) =
+                    make_uint4(pk[4], pk[5], pk[6], pk[7]);
               }
             }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && row0 < p.M) {
+              tma_store_3d(&tm_y, slab_base + ks_y * kSlabBytes, col_h, row0, j);
+              bulk_commit();
+              if (dual) {
+                tma_store_3d(&tm_y2, slab_base + ks_y2 * kSlabBytes, col_h, row0, j);
+                bulk_commit();
+              }
+            }
+            slab_k = (slab_k + n_out) % p.n_slabs;
+            if (dual && p.drop_mode == 1 && j == 0) {
+              // D(m) of the shared stream (LoRA dropout of the consuming fc2, drawn with seed + 1): derived from the
+              // bf16-rounded activation in the y2 slab so that it equals dropout(y2, seed + 1) exactly
+              const int ks_d = slab_k;
+              uint8_t* sd = slab_gen + ks_d * kSlabBytes;
+              if (lane == 0) bulk_wait_read<2>();  // only the two stores just issued may still be reading
+              __syncwarp();
+#pragma unroll 1
+              for (int gq = 0; gq < 4; ++gq) {
+                const int n0 = col_h + gq * 16;
+                if (n0 >= p.Nn) break;
+                const uint64_t e0 = static_cast<uint64_t>(grow) * p.Nn + n0;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  const uint4 mv = *reinterpret_cast<const uint4*>(sy2 + sw128_offset(lane, gq * 16 + hh * 8));
+                  const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+                  uint32_t ow[4];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i)
+                    ow[i] = dropout_apply_pair(mw[i], p.drop_seed + 1, e0 + hh * 8 + 2 * i, thr, keep_scale);
+                  *reinterpret_cast<uint4*>(sd + sw128_offset(lane, gq * 16 + hh * 8)) =
+                      make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                }
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0 && row0 < p.M) {
+                tma_store_3d(&tm_y2, slab_base + ks_d * kSlabBytes, col_h, row0, p.S_out);
+                bulk_commit();
+              }
+              slab_k = (slab_k + 1) % p.n_slabs;
+            }
           }
+          tc_fence_before();
+          mbar_arrive(d_empty(db));
         }
-        if (have_p) tmem_ld_wait();
+        if (multi) {
+          tc_fence_before();
+          mbar_arrive(p_empty(pb));
+          ++Cn;
+        }
       }
-      tc_fence_before();
-      mbar_arrive(acc_empty(b));
     }
+    if (lane == 0) bulk_wait_all();
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -458,47 +688,61 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
               p.R_pad, 16 * LIN_MAX_GRAN);
   MTL_REQUIRE(p.S_in >= 1 && p.S_in <= LIN_MAX_STREAMS && p.S_out >= 1 && p.S_out <= LIN_MAX_STREAMS,
               "linear: stream counts out of range");
-  MTL_REQUIRE(p.n_main > 0 || p.R_pad > 0, "linear: nothing to compute");
+  MTL_REQUIRE(p.n_main > 0, "linear: nothing to compute");
 
-  // ---- tiling -------------------------------------------------------------------------------
+  // ---- TMEM plan -------------------------------------------------------------------------------
+  // merged : one accumulator per item (dense + adapters), double-buffered between the two epilogue groups
+  // multi  : dense accumulator P per chunk (n_pbuf buffers) + per-stream delta accumulators D[2]
   const int u_cols = round_up(p.R_pad, 32);
-  p.n_regions = (p.S_out == 1 && !p.force_split && p.drop_mode != 2) ? 1 : 1 + p.S_out;
-  if (p.R_pad == 0 || p.n_main == 0) p.n_regions = (p.S_out == 1) ? 1 : 1 + p.S_out;
-  const int budget = 512 - u_cols;
-  const int n_round = round_up(p.Nn, 32);
-  auto fit_bn = [&](int n_acc) {
-    int bn = budget / (p.n_regions * n_acc) / 32 * 32;
-    if (bn > 128) bn = 128;
-    if (bn > n_round) bn = n_round;
-    return bn;
-  };
-  int bn = fit_bn(2);
-  p.n_acc = 2;
-  if (bn < 64 && fit_bn(1) > bn) {
-    bn = fit_bn(1);
-    p.n_acc = 1;
+  const bool multi = p.R_pad > 0 && (p.S_out > 1 || p.force_split || p.drop_mode == 2);
+  p.n_regions = multi ? 1 + p.S_out : 1;
+  p.n_pbuf = 0;
+  p.n_dbuf = 2;  // accumulators per epilogue group: 2 lets the MMA warp prepare a group's next item while it drains one
+  int bn = 64;
+  if (!multi) {
+    if (u_cols == 0 && p.Nn > 64) bn = 128;
+    if (u_cols + 4 * bn > 512) p.n_dbuf = 1;
+  } else {
+    p.n_pbuf = 2;
+    if (u_cols + (p.n_pbuf + 2 * p.n_dbuf) * bn > 512) p.n_pbuf = 1;
+    if (u_cols + (p.n_pbuf + 2 * p.n_dbuf) * bn > 512) { p.n_pbuf = 2; p.n_dbuf = 1; }
+    if (u_cols + (p.n_pbuf + 2 * p.n_dbuf) * bn > 512) p.n_pbuf = 1;
   }
-  MTL_REQUIRE(bn >= 32, "linear: TMEM budget exceeded (R_pad=%d, S_out=%d)", p.R_pad, p.S_out);
-  // even out the chunks: smallest multiple of 32 that keeps the chunk count
-  const int chunks = (p.Nn + bn - 1) / bn;
-  bn = round_up((p.Nn + chunks - 1) / chunks, 32);
   p.BN = bn;
   p.n_chunks = (p.Nn + bn - 1) / bn;
-  if (p.n_chunks == 1) p.n_acc = 1;
   p.acc_col0 = u_cols;
-  const int need_cols = u_cols + p.n_acc * p.n_regions * p.BN;
+  const int need_cols = u_cols + (p.n_pbuf + 2 * p.n_dbuf) * bn;
+  MTL_REQUIRE(need_cols <= 512, "linear: TMEM budget exceeded (R_pad=%d, S_out=%d)", p.R_pad, p.S_out);
   p.tmem_cols = 32;
   while (p.tmem_cols < need_cols) p.tmem_cols *= 2;
-  MTL_REQUIRE(p.tmem_cols <= 512, "linear: TMEM columns %d > 512", need_cols);
 
-  int max_len = p.BN;
-  for (int g = 0; g < p.n_groups; ++g) {
-    MTL_REQUIRE(p.grp_len[g] % 16 == 0 && p.grp_len[g] >= 16 && p.grp_len[g] <= 128,
-                "linear: down group length %d invalid", p.grp_len[g]);
-    if (p.grp_len[g] > max_len) max_len = p.grp_len[g];
+  // ---- phase-1 groups must fit the B half of a ring stage (BN rows) ----------------------------------------
+  {
+    const LinPlan q = p;
+    int n = 0;
+    for (int g = 0; g < q.n_groups; ++g) {
+      int r0 = q.grp_r0[g], len = q.grp_len[g];
+      MTL_REQUIRE(len % 16 == 0 && len >= 16, "linear: down group length %d invalid", len);
+      while (len > 0) {
+        MTL_REQUIRE(n < LIN_MAX_GROUPS, "linear: too many adapter groups");
+        const int l = len > bn ? bn : len;
+        p.grp_in[n] = q.grp_in[g];
+        p.grp_r0[n] = r0;
+        p.grp_len[n] = l;
+        p.grp_acc[n] = q.grp_acc[g];
+        ++n;
+        r0 += l;
+        len -= l;
+      }
+    }
+    p.n_groups = n;
   }
-  p.stage_b_bytes = round_up(max_len * 128, 1024);
+  p.stage_b_bytes = bn * 128;
+  const int stage_bytes = kTileABytes + p.stage_b_bytes;
+  const int n_uatoms = (p.R_pad + 63) / 64;
+  MTL_REQUIRE(n_uatoms <= kMaxUAtoms, "linear: too many rank atoms");
 
+  // ---- work decomposition: (128-row tile, column split), persistent CTAs ---------------------------------------
   const int m_tiles = (p.M + LIN_BM - 1) / LIN_BM;
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
@@ -508,17 +752,20 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
     p.n_splits = (2 * n_sm + m_tiles - 1) / m_tiles;
     if (p.n_splits > p.n_chunks) p.n_splits = p.n_chunks;
   }
+  p.n_work = m_tiles * p.n_splits;
 
-  // ring depth: as many stages as fit; keep <= ~100 KiB when TMEM allows two CTAs per SM
-  const int smem_cap = (p.tmem_cols <= 256) ? 110 * 1024 : 220 * 1024;
-  p.n_stages = 8;
-  while (p.n_stages > 2 && smem_layout(p.n_stages, p.stage_b_bytes, p.R_pad).total + 1024 > (uint32_t)smem_cap)
+  // ---- shared memory: store slabs + U operand + as many ring stages as fit ---------------------------------------
+  p.n_slabs = (p.ep_mode == LIN_EP_GELU_DUAL) ? 3 : 2;
+  const int min_stages = n_uatoms > 0 ? n_uatoms + 2 : 2;
+  p.n_stages = kMaxStages;
+  while (p.n_stages > min_stages &&
+         smem_layout(p.n_stages, stage_bytes, p.R_pad, p.n_slabs).total + 1024 > 227u * 1024)
     --p.n_stages;
-  const uint32_t smem_bytes = smem_layout(p.n_stages, p.stage_b_bytes, p.R_pad).total + 1024;
+  const uint32_t smem_bytes = smem_layout(p.n_stages, stage_bytes, p.R_pad, p.n_slabs).total + 1024;
   MTL_REQUIRE(smem_bytes <= 227 * 1024, "linear: shared memory %u exceeds 227 KiB", smem_bytes);
 
   // ---- tensor maps ---------------------------------------------------------------------------
-  CUtensorMap tm_x, tm_w, tm_down, tm_up;
+  CUtensorMap tm_x, tm_w, tm_down, tm_up, tm_y, tm_y2, tm_u;
   if (int e = make_tmap(&tm_x, x, p.Kc, p.M, p.S_in, LIN_BK, LIN_BM)) return e;
   if (int e = make_tmap(&tm_w, wm, p.Kc, p.Nn, 0, LIN_BK, p.BN)) return e;
   if (p.R_pad > 0) {
@@ -528,16 +775,34 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
     tm_down = tm_w;
     tm_up = tm_w;
   }
+  if (int e = make_tmap(&tm_y, p.y, p.Nn, p.M, p.S_out, 64, 32)) return e;
+  if (p.ep_mode == LIN_EP_GELU_DUAL) {
+    MTL_REQUIRE(p.y2 != nullptr, "linear: GELU epilogue needs y2");
+    if (int e = make_tmap(&tm_y2, p.y2, p.Nn, p.M, p.S_out + (p.drop_mode == 1 ? 1 : 0), 64, 32)) return e;
+  } else {
+    tm_y2 = tm_y;
+  }
+  if (p.u_save != nullptr && p.R_pad > 0) {
+    if (int e = make_tmap(&tm_u, p.u_save, p.R_pad, p.M, 0, 64, LIN_BM)) return e;
+  } else {
+    tm_u = tm_y;
+  }
 
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
+  static int max_ctas = -1;
   std::call_once(attr_once, []() {
     attr_err = cudaFuncSetAttribute(mtl_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    const char* e = getenv("MTL_LINEAR_MAX_CTAS");  // debugging aid: 0 = one CTA per work item (non-persistent)
+    max_ctas = e ? atoi(e) : -1;
   });
   MTL_CHECK_CUDA(attr_err);
 
-  const dim3 grid(m_tiles * p.n_splits);
-  mtl_linear_kernel<<<grid, kThreads, smem_bytes, stream>>>(tm_x, tm_w, tm_down, tm_up, p); note_launch();
+  int grid = p.n_work < n_sm ? p.n_work : n_sm;
+  if (max_ctas == 0) grid = p.n_work;
+  else if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  mtl_linear_kernel<<<grid, kThreads, smem_bytes, stream>>>(tm_x, tm_w, tm_down, tm_up, tm_y, tm_y2, tm_u, p);
+  note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -35,8 +35,11 @@ struct LinPlan {
   int n_splits;  // CTAs sharing one 128-row tile (each takes chunks split, split+n_splits, ...)
   int n_stages;  // TMA ring depth
   int stage_b_bytes;
-  int n_acc;      // accumulator buffers in TMEM (1 or 2)
-  int n_regions;  // regions per buffer: 1 (dense+adapter merged) or 1 + S_out
+  int n_regions;  // 1: dense + adapters merged in one accumulator per item; > 1: dense P + per-stream delta D
+  int n_pbuf;     // dense accumulator buffers P (multi mode): 2, or 1 when the rank space leaves no room
+  int n_dbuf;     // item accumulators per epilogue group (2, or 1 when TMEM is short)
+  int n_work;     // work items = row tiles x column splits (walked by persistent CTAs)
+  int n_slabs;    // per-epilogue-warp store slabs in shared memory
   int acc_col0;   // first accumulator column in TMEM
   int tmem_cols;  // allocation size (power of two >= 32)
 

@@ -87,14 +87,12 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const LnFwdParams p)
     *reinterpret_cast<uint4*>(p.y + off) =
         make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
     if (do_drop) {
+      // the dropped copy is derived from the bf16-rounded value so that it equals D(y) exactly
+      uint32_t d[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        // the dropped copy is derived from the bf16-rounded value so that it equals D(y) exactly
-        const float r = __bfloat162float(__float2bfloat16_rn(o[e]));
-        o[e] = dropout_hash(p.drop_seed, off + e) >= thr ? r * keep_scale : 0.f;
-      }
-      *reinterpret_cast<uint4*>(p.y_drop + off) =
-          make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+      for (int e = 0; e < 4; ++e)
+        d[e] = dropout_apply_pair(pack_bf16x2(o[2 * e], o[2 * e + 1]), p.drop_seed, off + 2 * e, thr, keep_scale);
+      *reinterpret_cast<uint4*>(p.y_drop + off) = make_uint4(d[0], d[1], d[2], d[3]);
     }
   }
 }
@@ -267,11 +265,7 @@ __global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
     uint32_t o[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float lo = dropout_hash(seed, v * 8 + 2 * e) >= thr ? bf16lo_to_f32(w[e]) * ks : 0.f;
-      const float hi = dropout_hash(seed, v * 8 + 2 * e + 1) >= thr ? bf16hi_to_f32(w[e]) * ks : 0.f;
-      o[e] = pack_bf16x2(lo, hi);
-    }
+    for (int e = 0; e < 4; ++e) o[e] = dropout_apply_pair(w[e], seed, static_cast<uint64_t>(v) * 8 + 2 * e, thr, ks);
     reinterpret_cast<uint4*>(y)[v] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }

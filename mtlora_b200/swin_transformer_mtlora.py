@@ -353,6 +353,7 @@ class _BlockFn(torch.autograd.Function):
         p_fc1, p_fc2 = _layer_p(blk.mlp.fc1, tr), _layer_p(blk.mlp.fc2, tr)
         s1, s2, s3 = (_new_seed(), _new_seed(), _new_seed()) if max(p_qkv, p_proj, p_fc1, p_fc2) > 0 else (0, 0, 0)
         need = any(ctx.needs_input_grad)
+        ctx.set_materialize_grads(False)   # unused output streams arrive as None, not as zero tensors
         eps1, eps2 = blk.norm1.eps, blk.norm2.eps
         n1w, n1b = (t.detach().float() for t in _ln_params(blk.norm1))
         n2w, n2b = (t.detach().float() for t in _ln_params(blk.norm2))
@@ -645,6 +646,7 @@ class _PatchMergeFn(torch.autograd.Function):
         rows = S * B * L // 4
         nw, nb = pm.norm.weight.detach().float(), pm.norm.bias.detach().float()
         need = any(ctx.needs_input_grad)
+        ctx.set_materialize_grads(False)
         h, mean, rstd = ops.layernorm_fwd(x, nw, nb, pm.norm.eps, merge_hw=(H, W), dropout_p=p, seed=seed, drop_rows=rows)
         y, _, sv = eng.forward(h.view(-1, rows, 4 * C), dropout_p=p, seed=seed, save=need)
         if need:
