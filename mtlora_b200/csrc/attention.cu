@@ -77,13 +77,13 @@ struct AttnParams {
   WinGeom g;
 };
 
-__global__ void __launch_bounds__(128) win_attn_fwd_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(128, 4) win_attn_fwd_kernel(const AttnParams p) {
   __shared__ __align__(16) __nv_bfloat16 Qs[NP * QS];
   __shared__ __align__(16) __nv_bfloat16 Ks[NP * QS];
   __shared__ __align__(16) __nv_bfloat16 Vs[NP * QS];
   __shared__ float bias_s[225];
   __shared__ int rows_s[NP];
-  __shared__ int reg_s[NP];
+  __shared__ __align__(8) int reg_s[NP];
 
   const int head = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -94,15 +94,40 @@ __global__ void __launch_bounds__(128) win_attn_fwd_kernel(const AttnParams p) {
   const int tbl = (2 * g.ws - 1) * (2 * g.ws - 1);
   for (int i = threadIdx.x; i < tbl; i += blockDim.x) bias_s[i] = p.rpb[i * p.nH + head];
   const int C3 = 3 * p.C;
+  __syncthreads();
+  // The (query, key) pairs a thread owns are the same for every window, so the relative-position bias of this head
+  // (swin_transformer_mtlora.py:202-207) is gathered once into registers, pre-multiplied by log2(e); padded key
+  // columns get -inf. Per window only the optional SW-MSA mask is added.
+  constexpr float kLog2e = 1.4426950408889634f;
+  const int i0 = warp * 16 + g4, i1 = i0 + 8;
+  float bias_r[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = (e < 2) ? i0 : i1;
+      const int j = nt * 8 + t4 * 2 + (e & 1);
+      float b = -INFINITY;
+      if (j < g.N) {
+        const int ic = i < g.N ? i : 0;
+        const int iy = ic / g.ws, ix = ic - iy * g.ws, jy = j / g.ws, jx = j - jy * g.ws;
+        b = bias_s[(iy - jy + g.ws - 1) * (2 * g.ws - 1) + (ix - jx + g.ws - 1)] * kLog2e;
+      }
+      bias_r[nt][e] = b;
+    }
+  }
+  const float scale2 = p.scale * kLog2e;
 
   for (int win = blockIdx.x; win < n_win; win += gridDim.x) {
     const int b = win / nW, wi = win - b * nW;
     const int wy = wi / g.nww, wx = wi - wy * g.nww;
+    // only windows in the last window row / column straddle the shift seam (:297-319)
+    const bool seam = p.mask == nullptr && g.shift > 0 && (wy == g.nwh - 1 || wx == g.nww - 1);
     __syncthreads();  // previous iteration done with smem
     if (threadIdx.x < NP) {
       const int i = threadIdx.x;
       rows_s[i] = i < g.N ? token_row(g, b, wy, wx, i) : -1;
-      reg_s[i] = (i < g.N && g.shift > 0) ? region_id(g, wy, wx, i) : 0;
+      reg_s[i] = (i < g.N && seam) ? region_id(g, wy, wx, i) : 0;
     }
     __syncthreads();
     // gather q,k,v rows of this head: 3 tiles x 64 rows x 4 chunks of 16 B
@@ -121,29 +146,39 @@ __global__ void __launch_bounds__(128) win_attn_fwd_kernel(const AttnParams p) {
     float s[8][4];
     scores_16x64(s, Qs, Ks, warp, lane);
 
-    // bias + mask + softmax on rows (warp*16 + g4) and (+8)
-    const int i0 = warp * 16 + g4, i1 = i0 + 8;
+    // bias + mask + softmax (base 2) on rows i0 and i1
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int i = (e < 2) ? i0 : i1;
-        const int j = nt * 8 + t4 * 2 + (e & 1);
-        float v = -INFINITY;
-        if (j < g.N) {
-          const int ic = i < g.N ? i : 0;
-          const int iy = ic / g.ws, ix = ic - iy * g.ws, jy = j / g.ws, jx = j - jy * g.ws;
-          v = s[nt][e] * p.scale + bias_s[(iy - jy + g.ws - 1) * (2 * g.ws - 1) + (ix - jx + g.ws - 1)];
-          if (p.mask != nullptr) {
-            if (i < g.N) v += p.mask[(static_cast<size_t>(win % p.n_mask) * g.N + i) * g.N + j];
-          } else if (g.shift > 0 && reg_s[ic] != reg_s[j]) {
-            v += -100.0f;
-          }
+      for (int e = 0; e < 4; ++e) s[nt][e] = fmaf(s[nt][e], scale2, bias_r[nt][e]);
+    }
+    if (p.mask != nullptr) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = (e < 2) ? i0 : i1;
+          const int j = nt * 8 + t4 * 2 + (e & 1);
+          if (i < g.N && j < g.N)
+            s[nt][e] += p.mask[(static_cast<size_t>(win % p.n_mask) * g.N + i) * g.N + j] * kLog2e;
         }
-        s[nt][e] = v;
-        if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
       }
+    } else if (seam) {
+      const int r0 = reg_s[i0], r1 = reg_s[i1];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int2 rj = *reinterpret_cast<const int2*>(&reg_s[nt * 8 + t4 * 2]);
+        if (r0 != rj.x) s[nt][0] += -100.0f * kLog2e;
+        if (r0 != rj.y) s[nt][1] += -100.0f * kLog2e;
+        if (r1 != rj.x) s[nt][2] += -100.0f * kLog2e;
+        if (r1 != rj.y) s[nt][3] += -100.0f * kLog2e;
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
     }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
@@ -155,7 +190,7 @@ __global__ void __launch_bounds__(128) win_attn_fwd_kernel(const AttnParams p) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float m = (e < 2) ? mx0 : mx1;
-        const float pv = __expf(s[nt][e] - m);
+        const float pv = exp2f(s[nt][e] - m);
         s[nt][e] = pv;
         if (e < 2) sum0 += pv; else sum1 += pv;
       }
@@ -167,8 +202,8 @@ __global__ void __launch_bounds__(128) win_attn_fwd_kernel(const AttnParams p) {
     const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
     if (p.lse != nullptr && t4 == 0) {
       float* l = p.lse + (static_cast<size_t>(win) * p.nH + head) * NP;
-      l[i0] = mx0 + __logf(sum0);
-      l[i1] = mx1 + __logf(sum1);
+      l[i0] = (mx0 + log2f(sum0)) * 0.6931471805599453f;   // natural-log units
+      l[i1] = (mx1 + log2f(sum1)) * 0.6931471805599453f;
     }
 
     // O = P V  (P from registers, V via transposed ldmatrix)
@@ -232,7 +267,7 @@ struct AttnBwdParams {
   WinGeom g;
 };
 
-__global__ void __launch_bounds__(128) win_attn_bwd_kernel(const AttnBwdParams p) {
+__global__ void __launch_bounds__(128, 3) win_attn_bwd_kernel(const AttnBwdParams p) {
   __shared__ __align__(16) __nv_bfloat16 Qs[NP * QS];
   __shared__ __align__(16) __nv_bfloat16 Ks[NP * QS];
   __shared__ __align__(16) __nv_bfloat16 Vs[NP * QS];
@@ -242,7 +277,7 @@ __global__ void __launch_bounds__(128) win_attn_bwd_kernel(const AttnBwdParams p
   __shared__ float bias_s[225];
   __shared__ float dbias_s[225];
   __shared__ int rows_s[NP];
-  __shared__ int reg_s[NP];
+  __shared__ __align__(8) int reg_s[NP];
 
   const int head = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -259,15 +294,37 @@ __global__ void __launch_bounds__(128) win_attn_bwd_kernel(const AttnBwdParams p
   float dsacc[8][4];  // sum over this CTA's windows of dS (for d relative_position_bias_table)
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) dsacc[nt][0] = dsacc[nt][1] = dsacc[nt][2] = dsacc[nt][3] = 0.f;
+  __syncthreads();
+  // per-thread relative-position bias (log2 units), gathered once: the owned (query, key) pairs never change
+  constexpr float kLog2e = 1.4426950408889634f;
+  const int i0 = warp * 16 + g4, i1 = i0 + 8;
+  float bias_r[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = (e < 2) ? i0 : i1;
+      const int j = nt * 8 + t4 * 2 + (e & 1);
+      float b = -INFINITY;
+      if (j < g.N) {
+        const int ic = i < g.N ? i : 0;
+        const int iy = ic / g.ws, ix = ic - iy * g.ws, jy = j / g.ws, jx = j - jy * g.ws;
+        b = bias_s[(iy - jy + g.ws - 1) * (2 * g.ws - 1) + (ix - jx + g.ws - 1)] * kLog2e;
+      }
+      bias_r[nt][e] = b;
+    }
+  }
+  const float scale2 = p.scale * kLog2e;
 
   for (int win = blockIdx.x; win < n_win; win += gridDim.x) {
     const int b = win / nW, wi = win - b * nW;
     const int wy = wi / g.nww, wx = wi - wy * g.nww;
+    const bool seam = p.mask == nullptr && g.shift > 0 && (wy == g.nwh - 1 || wx == g.nww - 1);
     __syncthreads();
     if (threadIdx.x < NP) {
       const int i = threadIdx.x;
       rows_s[i] = i < g.N ? token_row(g, b, wy, wx, i) : -1;
-      reg_s[i] = (i < g.N && g.shift > 0) ? region_id(g, wy, wx, i) : 0;
+      reg_s[i] = (i < g.N && seam) ? region_id(g, wy, wx, i) : 0;
     }
     __syncthreads();
     for (int idx = threadIdx.x; idx < 4 * NP * 4; idx += blockDim.x) {
@@ -293,25 +350,42 @@ __global__ void __launch_bounds__(128) win_attn_bwd_kernel(const AttnBwdParams p
     // ---- recompute P = exp(S - lse) --------------------------------------------------------
     float s[8][4];
     scores_16x64(s, Qs, Ks, warp, lane);
-    const int i0 = warp * 16 + g4, i1 = i0 + 8;
     const float* l = p.lse + (static_cast<size_t>(win) * p.nH + head) * NP;
-    const float lse0 = l[i0], lse1 = l[i1];
+    // padded query rows: lse = +inf -> P = 0
+    const float lse0 = i0 < g.N ? l[i0] * kLog2e : INFINITY, lse1 = i1 < g.N ? l[i1] * kLog2e : INFINITY;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int i = (e < 2) ? i0 : i1;
-        const int j = nt * 8 + t4 * 2 + (e & 1);
-        float pv = 0.f;
-        if (j < g.N && i < g.N) {
-          const int iy = i / g.ws, ix = i - iy * g.ws, jy = j / g.ws, jx = j - jy * g.ws;
-          float v = s[nt][e] * p.scale + bias_s[(iy - jy + g.ws - 1) * (2 * g.ws - 1) + (ix - jx + g.ws - 1)];
-          if (p.mask != nullptr) v += p.mask[(static_cast<size_t>(win % p.n_mask) * g.N + i) * g.N + j];
-          else if (g.shift > 0 && reg_s[i] != reg_s[j]) v += -100.0f;
-          pv = __expf(v - ((e < 2) ? lse0 : lse1));
+      for (int e = 0; e < 4; ++e) s[nt][e] = fmaf(s[nt][e], scale2, bias_r[nt][e]);
+    }
+    if (p.mask != nullptr) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = (e < 2) ? i0 : i1;
+          const int j = nt * 8 + t4 * 2 + (e & 1);
+          if (i < g.N && j < g.N)
+            s[nt][e] += p.mask[(static_cast<size_t>(win % p.n_mask) * g.N + i) * g.N + j] * kLog2e;
         }
-        s[nt][e] = pv;
       }
+    } else if (seam) {
+      const int r0 = reg_s[i0], r1 = reg_s[i1];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int2 rj = *reinterpret_cast<const int2*>(&reg_s[nt * 8 + t4 * 2]);
+        if (r0 != rj.x) s[nt][0] += -100.0f * kLog2e;
+        if (r0 != rj.y) s[nt][1] += -100.0f * kLog2e;
+        if (r1 != rj.x) s[nt][2] += -100.0f * kLog2e;
+        if (r1 != rj.y) s[nt][3] += -100.0f * kLog2e;
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = exp2f(s[nt][0] - lse0);
+      s[nt][1] = exp2f(s[nt][1] - lse0);
+      s[nt][2] = exp2f(s[nt][2] - lse1);
+      s[nt][3] = exp2f(s[nt][3] - lse1);
     }
     // ---- dP = dO V^T -------------------------------------------------------------------------
     float dp[8][4];
@@ -419,7 +493,6 @@ __global__ void __launch_bounds__(128) win_attn_bwd_kernel(const AttnBwdParams p
 
   if (p.drpb != nullptr) {
     __syncthreads();
-    const int i0 = warp * 16 + g4, i1 = i0 + 8;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
@@ -490,7 +563,7 @@ int launch_win_attn_bwd(const void* qkv, const void* dout, const float* rpb, con
   p.g = WinGeom{H, W, ws, shift, H / ws, W / ws, ws * ws};
   const int n_win = B * p.g.nwh * p.g.nww;
   int gx = n_win;
-  const int cap = (148 * 4 + nH - 1) / nH;
+  const int cap = (148 * 3 + nH - 1) / nH;  // 3 resident CTAs per SM (register-limited), strided over windows
   if (gx > cap) gx = cap;
   win_attn_bwd_kernel<<<dim3(gx, nH), 128, 0, stream>>>(p); note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());

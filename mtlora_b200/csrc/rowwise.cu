@@ -228,6 +228,263 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdParams p)
   }
 }
 
+// ---- fast LayerNorm for the Swin channel counts --------------------------------------------------------------------
+// A row of C = LPR * VPT * 8 channels is owned by LPR lanes (a power of two <= 32) holding VPT 16-byte vectors each, so
+// a warp normalises 32 / LPR rows at once with every lane busy (the one-warp-per-row kernels above leave 20 of 32 lanes
+// idle at C = 96). The row lives in registers between the statistics and the output pass (one HBM read), gamma / beta
+// are loaded once per thread, and the backward keeps the per-column dgamma / dbeta partial sums in registers over all
+// the rows a lane visits.
+template <int LPR>
+__device__ __forceinline__ float subwarp_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int LPR, int VPT>
+__global__ void __launch_bounds__(256, 2) ln_fwd_fast_kernel(const LnFwdParams p) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR, rsel = lane / LPR;
+  const long warp_g = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long n_warps = static_cast<long>(gridDim.x) * (blockDim.x >> 5);
+  const int Cs = p.merge ? p.C >> 2 : p.C;
+  const int vec_per_seg = Cs >> 3;
+  float gam[VPT][8], bet[VPT][8];
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int v = sub + k * LPR;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * v);
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * v + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta) + 2 * v);
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.beta) + 2 * v + 1);
+    gam[k][0] = g0.x; gam[k][1] = g0.y; gam[k][2] = g0.z; gam[k][3] = g0.w;
+    gam[k][4] = g1.x; gam[k][5] = g1.y; gam[k][6] = g1.z; gam[k][7] = g1.w;
+    bet[k][0] = b0.x; bet[k][1] = b0.y; bet[k][2] = b0.z; bet[k][3] = b0.w;
+    bet[k][4] = b1.x; bet[k][5] = b1.y; bet[k][6] = b1.z; bet[k][7] = b1.w;
+  }
+  const uint32_t thr = dropout_threshold(p.drop_p);
+  const float inv_c = 1.f / p.C;
+  for (long rg = warp_g; rg * RPW < p.rows; rg += n_warps) {
+    const long row = rg * RPW + rsel;
+    const bool ok = row < p.rows;
+    float xv[VPT][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int v = sub + k * LPR;
+      uint4 q = make_uint4(0, 0, 0, 0);
+      if (ok) {
+        const __nv_bfloat16* src;
+        if (!p.merge) {
+          src = p.x + row * p.C + v * 8;
+        } else {
+          const int seg = v / vec_per_seg;
+          src = p.x + merge_src_row(row, seg, p.H, p.W) * Cs + (v - seg * vec_per_seg) * 8;
+        }
+        q = __ldg(reinterpret_cast<const uint4*>(src));
+      }
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        xv[k][2 * e] = bf16lo_to_f32(w[e]);
+        xv[k][2 * e + 1] = bf16hi_to_f32(w[e]);
+        sum += xv[k][2 * e] + xv[k][2 * e + 1];
+      }
+    }
+    const float mean = subwarp_sum<LPR>(sum) * inv_c;
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = xv[k][e] - mean;
+        sq += d * d;
+      }
+    const float rstd = rsqrtf(subwarp_sum<LPR>(sq) * inv_c + p.eps);
+    if (!ok) continue;
+    if (sub == 0) {
+      if (p.mean) p.mean[row] = mean;
+      if (p.rstd) p.rstd[row] = rstd;
+    }
+    const bool do_drop = p.y_drop != nullptr && row < p.drop_rows;
+    const float keep_scale = 1.f / (1.f - p.drop_p);
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int v = sub + k * LPR;
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        o[e] = pack_bf16x2((xv[k][2 * e] - mean) * rstd * gam[k][2 * e] + bet[k][2 * e],
+                           (xv[k][2 * e + 1] - mean) * rstd * gam[k][2 * e + 1] + bet[k][2 * e + 1]);
+      const size_t off = static_cast<size_t>(row) * p.C + v * 8;
+      *reinterpret_cast<uint4*>(p.y + off) = make_uint4(o[0], o[1], o[2], o[3]);
+      if (do_drop) {
+        uint32_t d[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) d[e] = dropout_apply_pair(o[e], p.drop_seed, off + 2 * e, thr, keep_scale);
+        *reinterpret_cast<uint4*>(p.y_drop + off) = make_uint4(d[0], d[1], d[2], d[3]);
+      }
+    }
+  }
+}
+
+template <int LPR, int VPT, bool PARAM_GRADS>
+__global__ void __launch_bounds__(256, 2) ln_bwd_fast_kernel(const LnBwdParams p) {
+  extern __shared__ float red[];  // [2][C]
+  constexpr int RPW = 32 / LPR;
+  if (PARAM_GRADS) {
+    for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR, rsel = lane / LPR;
+  const long warp_g = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long n_warps = static_cast<long>(gridDim.x) * (blockDim.x >> 5);
+  const int Cs = p.merge ? p.C >> 2 : p.C;
+  const int vec_per_seg = Cs >> 3;
+  float gam[VPT][8];
+  float dg[PARAM_GRADS ? VPT : 1][8], db[PARAM_GRADS ? VPT : 1][8];
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int v = sub + k * LPR;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * v);
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * v + 1);
+    gam[k][0] = g0.x; gam[k][1] = g0.y; gam[k][2] = g0.z; gam[k][3] = g0.w;
+    gam[k][4] = g1.x; gam[k][5] = g1.y; gam[k][6] = g1.z; gam[k][7] = g1.w;
+    if (PARAM_GRADS) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dg[k][e] = db[k][e] = 0.f;
+    }
+  }
+  const float inv_c = 1.f / p.C;
+  for (long rg = warp_g; rg * RPW < p.rows; rg += n_warps) {
+    const long row = rg * RPW + rsel;
+    const bool ok = row < p.rows;
+    const float mean = ok ? p.mean[row] : 0.f, rstd = ok ? p.rstd[row] : 0.f;
+    uint4 qx[VPT], qd[VPT];   // the row stays packed in registers between the two passes
+    size_t soff[VPT];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int v = sub + k * LPR;
+      qx[k] = make_uint4(0, 0, 0, 0);
+      qd[k] = make_uint4(0, 0, 0, 0);
+      soff[k] = 0;
+      if (ok) {
+        if (!p.merge) {
+          soff[k] = static_cast<size_t>(row) * p.C + v * 8;
+        } else {
+          const int seg = v / vec_per_seg;
+          soff[k] = static_cast<size_t>(merge_src_row(row, seg, p.H, p.W)) * Cs + (v - seg * vec_per_seg) * 8;
+        }
+        qx[k] = __ldg(reinterpret_cast<const uint4*>(p.x + soff[k]));
+        qd[k] = __ldg(reinterpret_cast<const uint4*>(p.dy + static_cast<size_t>(row) * p.C + v * 8));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const uint32_t wx[4] = {qx[k].x, qx[k].y, qx[k].z, qx[k].w}, wd[4] = {qd[k].x, qd[k].y, qd[k].z, qd[k].w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float x = (e & 1) ? bf16hi_to_f32(wx[e >> 1]) : bf16lo_to_f32(wx[e >> 1]);
+        const float d = (e & 1) ? bf16hi_to_f32(wd[e >> 1]) : bf16lo_to_f32(wd[e >> 1]);
+        const float h = (x - mean) * rstd;
+        const float g = d * gam[k][e];
+        s1 += g;
+        s2 += g * h;
+        if (PARAM_GRADS) {
+          dg[k][e] += d * h;
+          db[k][e] += d;
+        }
+      }
+    }
+    s1 = subwarp_sum<LPR>(s1) * inv_c;
+    s2 = subwarp_sum<LPR>(s2) * inv_c;
+    if (!ok) continue;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      uint32_t wr[4] = {0, 0, 0, 0};
+      if (p.dres) {
+        const uint4 qr = __ldg(reinterpret_cast<const uint4*>(p.dres + soff[k]));
+        wr[0] = qr.x; wr[1] = qr.y; wr[2] = qr.z; wr[3] = qr.w;
+      }
+      const uint32_t wx[4] = {qx[k].x, qx[k].y, qx[k].z, qx[k].w}, wd[4] = {qd[k].x, qd[k].y, qd[k].z, qd[k].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float h0 = (bf16lo_to_f32(wx[e]) - mean) * rstd, h1 = (bf16hi_to_f32(wx[e]) - mean) * rstd;
+        const float g0 = bf16lo_to_f32(wd[e]) * gam[k][2 * e], g1 = bf16hi_to_f32(wd[e]) * gam[k][2 * e + 1];
+        o[e] = pack_bf16x2(rstd * (g0 - s1 - h0 * s2) + bf16lo_to_f32(wr[e]),
+                           rstd * (g1 - s1 - h1 * s2) + bf16hi_to_f32(wr[e]));
+      }
+      *reinterpret_cast<uint4*>(p.dx + soff[k]) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  if (PARAM_GRADS) {
+    // lanes with the same `sub` own the same columns: fold the RPW row slots of the warp, then warp -> CTA -> global
+#pragma unroll
+    for (int k = 0; k < VPT; ++k)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float a = dg[k][e], b = db[k][e];
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (rsel == 0) {
+          atomicAdd(&red[(sub + k * LPR) * 8 + e], a);
+          atomicAdd(&red[p.C + (sub + k * LPR) * 8 + e], b);
+        }
+      }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.C; i += blockDim.x) {
+      atomicAdd(p.dgamma + i, red[i]);
+      atomicAdd(p.dbeta + i, red[p.C + i]);
+    }
+  }
+}
+
+// (lanes per row, vectors per lane) for the channel counts of Swin-T/S (96 * 2^s, x4 for PatchMerging) and Swin-B
+// (128 * 2^s); anything else (or very wide rows) takes the generic one-warp-per-row kernels.
+static bool ln_fast_shape(int C, int* lpr, int* vpt) {
+  switch (C) {
+    case 96: *lpr = 4; *vpt = 3; return true;
+    case 192: *lpr = 8; *vpt = 3; return true;
+    case 384: *lpr = 16; *vpt = 3; return true;
+    case 768: *lpr = 32; *vpt = 3; return true;
+    case 128: *lpr = 8; *vpt = 2; return true;
+    case 256: *lpr = 16; *vpt = 2; return true;
+    case 512: *lpr = 32; *vpt = 2; return true;
+    case 1024: *lpr = 32; *vpt = 4; return true;
+    default: return false;
+  }
+}
+
+template <int LPR, int VPT>
+static void ln_fwd_launch(const LnFwdParams& p, unsigned grid, cudaStream_t stream) {
+  ln_fwd_fast_kernel<LPR, VPT><<<grid, 256, 0, stream>>>(p);
+}
+template <int LPR, int VPT>
+static void ln_bwd_launch(const LnBwdParams& p, unsigned grid, cudaStream_t stream) {
+  const size_t sm = 2 * p.C * sizeof(float);
+  if (p.dgamma) ln_bwd_fast_kernel<LPR, VPT, true><<<grid, 256, sm, stream>>>(p);
+  else ln_bwd_fast_kernel<LPR, VPT, false><<<grid, 256, sm, stream>>>(p);
+}
+#define MTL_LN_CASES(FN, ...)                      \
+  switch (lpr * 100 + vpt) {                       \
+    case 403: FN<4, 3>(__VA_ARGS__); break;        \
+    case 803: FN<8, 3>(__VA_ARGS__); break;        \
+    case 1603: FN<16, 3>(__VA_ARGS__); break;      \
+    case 3203: FN<32, 3>(__VA_ARGS__); break;      \
+    case 802: FN<8, 2>(__VA_ARGS__); break;        \
+    case 1602: FN<16, 2>(__VA_ARGS__); break;      \
+    case 3202: FN<32, 2>(__VA_ARGS__); break;      \
+    case 3204: FN<32, 4>(__VA_ARGS__); break;      \
+    default: break;                                \
+  }
+
 // ---- kernels/window_process equivalents ----------------------------------------------------------
 // partition: out[b*nWin + wy*nW + wx, iy, ix, :] = in[b, (wy*ws+iy+shift) % H, (wx*ws+ix+shift) % W, :]
 // (torch.roll(x, (-shift,-shift)) + window_partition). `scatter` swaps source and destination, which is both
@@ -400,8 +657,18 @@ int launch_layernorm_fwd(const void* x, const float* gamma, const float* beta, v
   MTL_REQUIRE(!merge || (H % 2 == 0 && W % 2 == 0), "patch merging: x size (%d*%d) are not even.", H, W);
   LnFwdParams p{static_cast<const __nv_bfloat16*>(x), gamma, beta, static_cast<__nv_bfloat16*>(y),
                 static_cast<__nv_bfloat16*>(y_drop), mean, rstd, rows, drop_rows, C, merge, H, W, eps, drop_p, drop_seed};
-  const int wpb = 8;
-  layernorm_fwd_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(p); note_launch();
+  int lpr = 0, vpt = 0;
+  if (ln_fast_shape(C, &lpr, &vpt)) {
+    const long row_groups = (rows + (32 / lpr) - 1) / (32 / lpr);
+    long grid = (row_groups + 7) / 8;
+    if (grid > 148L * 8) grid = 148L * 8;
+    const unsigned g = static_cast<unsigned>(grid);
+    MTL_LN_CASES(ln_fwd_launch, p, g, stream)
+  } else {
+    const int wpb = 8;
+    layernorm_fwd_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(p);
+  }
+  note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -415,6 +682,17 @@ int launch_layernorm_bwd(const void* dy, const void* x, const float* gamma, cons
   LnBwdParams p{static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), gamma, mean, rstd,
                 static_cast<const __nv_bfloat16*>(dres), static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, rows, C,
                 merge, H, W, 0};
+  int lpr = 0, vpt = 0;
+  if (ln_fast_shape(C, &lpr, &vpt)) {
+    const long row_groups = (rows + (32 / lpr) - 1) / (32 / lpr);
+    long grid = (row_groups + 7) / 8;
+    if (grid > 148L * 4) grid = 148L * 4;
+    const unsigned g = static_cast<unsigned>(grid);
+    MTL_LN_CASES(ln_bwd_launch, p, g, stream)
+    note_launch();
+    MTL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   long ctas = 148L * 4;
   long rpc = (rows + ctas - 1) / ctas;
   if (rpc < 8) rpc = 8;
