@@ -141,6 +141,9 @@ __device__ __forceinline__ WorkItem get_work(const LinPlan& p, int w) {
   return it;
 }
 
+// EP: LinEpilogue; HAS_RES: a residual tensor is added in the epilogue (compile-time specialisation keeps the
+// per-element instruction count of the epilogue — the bottleneck of the wide stage-0/1 layers — minimal)
+template <int EP, bool HAS_RES>
 __global__ void __launch_bounds__(kThreads, 1)
 mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                   const __grid_constant__ CUtensorMap tm_down, const __grid_constant__ CUtensorMap tm_up,
@@ -417,7 +420,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const uint32_t thr = dropout_threshold(p.drop_p);
     const float keep_scale = 1.f / (1.f - p.drop_p);
     const size_t stream_stride = static_cast<size_t>(p.M) * p.Nn;
-    const bool dual = p.ep_mode == LIN_EP_GELU_DUAL;
+    constexpr bool dual = EP == LIN_EP_GELU_DUAL;
 
     uint32_t lw = 0, Cn = 0, G = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++lw) {
@@ -472,6 +475,27 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         for (int j = 0; j < n_items; ++j, ++G) {
           if ((G & 1u) != grp) continue;
           const uint32_t kk = G >> 1, dbuf = kk % p.n_dbuf, db = grp * 2 + dbuf;
+          // epilogue inputs that do not depend on the accumulators (GELU' argument, residual) are fetched one
+          // 16-column granule ahead; the first granule's loads are issued before waiting for the MMAs
+          constexpr bool need_aux = EP == LIN_EP_GELU_BWD, need_res = HAS_RES;
+          const size_t row_off = static_cast<size_t>(grow) * p.Nn;
+          const __nv_bfloat16* aux_row = need_aux ? p.aux + j * stream_stride + row_off : nullptr;
+          const __nv_bfloat16* res_row =
+              need_res ? p.res + (p.res_streams == 1 ? 0 : j * stream_stride) + row_off : nullptr;
+          uint4 na0 = make_uint4(0, 0, 0, 0), na1 = na0, nr0 = na0, nr1 = na0;
+          auto fetch_extra = [&](int n0) {
+            if (row_ok && n0 < p.Nn) {
+              if (need_aux) {
+                na0 = __ldg(reinterpret_cast<const uint4*>(aux_row + n0));
+                na1 = __ldg(reinterpret_cast<const uint4*>(aux_row + n0) + 1);
+              }
+              if (need_res) {
+                nr0 = __ldg(reinterpret_cast<const uint4*>(res_row + n0));
+                nr1 = __ldg(reinterpret_cast<const uint4*>(res_row + n0) + 1);
+              }
+            }
+          };
+          fetch_extra(c * p.BN);
           mbar_wait(d_full(db), (kk / p.n_dbuf) & 1u);
           const bool use_p = multi && p.out_useP[j];
           if (use_p && !p_waited) {
@@ -488,9 +512,11 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             const int col_h = c * p.BN + h * 64;
             // slabs of this half: y -> ks_y, GELU(y) -> ks_y2. A slab is reused every n_slabs stores; with at most
             // n_slabs - n_out bulk groups still pending the ones that used these slabs have been read.
-            if (lane == 0) bulk_wait_read<1>();
+            constexpr int n_out = dual ? 2 : 1;
+            if (lane == 0) {
+              if (p.n_slabs - n_out >= 1) bulk_wait_read<1>(); else bulk_wait_read<0>();
+            }
             __syncwarp();
-            const int n_out = dual ? 2 : 1;
             const int ks_y = slab_k;
             const int ks_y2 = (slab_k + 1) % p.n_slabs;
             uint8_t* sy = slab_gen + ks_y * kSlabBytes;
@@ -529,11 +555,10 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] *= rs;
               }
-              if (row_ok) {
-                const size_t off = j * stream_stride + static_cast<size_t>(grow) * p.Nn + n0;
-                if (p.ep_mode == LIN_EP_GELU_BWD) {
-                  const uint4* ap = reinterpret_cast<const uint4*>(p.aux + off);
-                  const uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
+              {
+                const uint4 a0 = na0, a1 = na1, r0 = nr0, r1 = nr1;
+                fetch_extra(n0 + 16);   // next granule (crosses into the next 64-column half when gq == 3)
+                if (need_aux) {
                   const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
@@ -543,11 +568,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     v[2 * i + 1] *= d1;
                   }
                 }
-                if (p.res != nullptr) {
-                  const size_t roff =
-                      (p.res_streams == 1 ? 0 : j * stream_stride) + static_cast<size_t>(grow) * p.Nn + n0;
-                  const uint4* rp = reinterpret_cast<const uint4*>(p.res + roff);
-                  const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                if (need_res) {
                   const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
@@ -589,7 +610,9 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               // bf16-rounded activation in the y2 slab so that it equals dropout(y2, seed + 1) exactly
               const int ks_d = slab_k;
               uint8_t* sd = slab_gen + ks_d * kSlabBytes;
-              if (lane == 0) bulk_wait_read<2>();  // only the two stores just issued may still be reading
+              if (lane == 0) {   // all but the (n_slabs - 1) most recent stores have been read
+                if (p.n_slabs >= 3) bulk_wait_read<2>(); else bulk_wait_read<1>();
+              }
               __syncwarp();
 #pragma unroll 1
               for (int gq = 0; gq < 4; ++gq) {
@@ -696,14 +719,29 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
   const int u_cols = round_up(p.R_pad, 32);
   const bool multi = p.R_pad > 0 && (p.S_out > 1 || p.force_split || p.drop_mode == 2);
   p.n_regions = multi ? 1 + p.S_out : 1;
+  // Column-chunk width BN and accumulator buffering. Short contractions (K_eff < 256: stages 0-1) are epilogue / HBM
+  // bound: narrow chunks, two accumulators per epilogue group so the MMA warp runs ahead. Long contractions are
+  // bound by operand traffic (every chunk re-streams the X tile from L2): wide chunks, one accumulator per group.
+  const bool heavy = p.Kc >= 256;
   p.n_pbuf = 0;
-  p.n_dbuf = 2;  // accumulators per epilogue group: 2 lets the MMA warp prepare a group's next item while it drains one
+  p.n_dbuf = 2;
   int bn = 64;
   if (!multi) {
-    if (u_cols == 0 && p.Nn > 64) bn = 128;
-    if (u_cols + 4 * bn > 512) p.n_dbuf = 1;
+    if (heavy && p.Nn > 64) {
+      p.n_dbuf = 1;
+      bn = (p.Nn > 128 && u_cols + 2 * 192 <= 512) ? 192 : 128;
+      if (u_cols + 2 * bn > 512) bn = 64;
+    } else if (u_cols == 0 && p.Nn > 64) {
+      bn = 128;
+    }
+    if (u_cols + 2 * p.n_dbuf * bn > 512) p.n_dbuf = 1;
   } else {
     p.n_pbuf = 2;
+    if (heavy && p.Nn > 64 && u_cols + 3 * 128 <= 512) {
+      bn = 128;
+      p.n_pbuf = 1;
+      p.n_dbuf = 1;
+    }
     if (u_cols + (p.n_pbuf + 2 * p.n_dbuf) * bn > 512) p.n_pbuf = 1;
     if (u_cols + (p.n_pbuf + 2 * p.n_dbuf) * bn > 512) { p.n_pbuf = 2; p.n_dbuf = 1; }
     if (u_cols + (p.n_pbuf + 2 * p.n_dbuf) * bn > 512) p.n_pbuf = 1;
@@ -747,16 +785,30 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  // Column splits: with few row tiles, split the chunks of a tile over several work items so that the persistent
+  // grid is balanced (every split repeats the rank-space phase, modelled as one extra 64-column chunk).
   p.n_splits = 1;
-  if (m_tiles < 2 * n_sm) {
-    p.n_splits = (2 * n_sm + m_tiles - 1) / m_tiles;
-    if (p.n_splits > p.n_chunks) p.n_splits = p.n_chunks;
+  if (m_tiles < 4 * n_sm && p.n_chunks > 1) {
+    double best = -1.0;
+    for (int sp = 1; sp <= p.n_chunks; ++sp) {
+      const long work = static_cast<long>(m_tiles) * sp;
+      const long waves = (work + n_sm - 1) / n_sm;
+      const int chunks_max = (p.n_chunks + sp - 1) / sp;                       // chunks of the largest split
+      const double item_cost = chunks_max * static_cast<double>(bn) + (p.R_pad > 0 ? 64.0 : 0.0) + 16.0;
+      const double t = waves * item_cost;                                      // ~ time of the slowest CTA
+      const double score = 1.0 / t;
+      if (score > best * 1.0001) {
+        best = score;
+        p.n_splits = sp;
+      }
+    }
   }
   p.n_work = m_tiles * p.n_splits;
 
   // ---- shared memory: store slabs + U operand + as many ring stages as fit ---------------------------------------
   p.n_slabs = (p.ep_mode == LIN_EP_GELU_DUAL) ? 3 : 2;
   const int min_stages = n_uatoms > 0 ? n_uatoms + 2 : 2;
+  if (smem_layout(min_stages, stage_bytes, p.R_pad, p.n_slabs).total + 1024 > 227u * 1024) p.n_slabs = 2;
   p.n_stages = kMaxStages;
   while (p.n_stages > min_stages &&
          smem_layout(p.n_stages, stage_bytes, p.R_pad, p.n_slabs).total + 1024 > 227u * 1024)
@@ -788,20 +840,32 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
     tm_u = tm_y;
   }
 
+  using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
+                            LinPlan);
+  static KernelFn kernels[3][2] = {
+      {mtl_linear_kernel<LIN_EP_NONE, false>, mtl_linear_kernel<LIN_EP_NONE, true>},
+      {mtl_linear_kernel<LIN_EP_GELU_DUAL, false>, mtl_linear_kernel<LIN_EP_GELU_DUAL, true>},
+      {mtl_linear_kernel<LIN_EP_GELU_BWD, false>, mtl_linear_kernel<LIN_EP_GELU_BWD, true>}};
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   static int max_ctas = -1;
   std::call_once(attr_once, []() {
-    attr_err = cudaFuncSetAttribute(mtl_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 2; ++b) {
+        cudaError_t e = cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) attr_err = e;
+      }
     const char* e = getenv("MTL_LINEAR_MAX_CTAS");  // debugging aid: 0 = one CTA per work item (non-persistent)
     max_ctas = e ? atoi(e) : -1;
   });
   MTL_CHECK_CUDA(attr_err);
+  MTL_REQUIRE(p.ep_mode >= 0 && p.ep_mode <= 2, "linear: unknown epilogue mode %d", p.ep_mode);
 
   int grid = p.n_work < n_sm ? p.n_work : n_sm;
   if (max_ctas == 0) grid = p.n_work;
   else if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  mtl_linear_kernel<<<grid, kThreads, smem_bytes, stream>>>(tm_x, tm_w, tm_down, tm_up, tm_y, tm_y2, tm_u, p);
+  kernels[p.ep_mode][p.res != nullptr ? 1 : 0]<<<grid, kThreads, smem_bytes, stream>>>(tm_x, tm_w, tm_down, tm_up, tm_y,
+                                                                                      tm_y2, tm_u, p);
   note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
   return 0;
