@@ -141,11 +141,14 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
 }
 // Bounded wait: a protocol bug must trap (surfacing as a CUDA error) instead of hanging the GPU. The timer is only
 // consulted every 4096 unsuccessful polls so that waiting warps do not compete with working warps for issue slots.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifndef MTL_WAIT_HINT_NS
+#define MTL_WAIT_HINT_NS 20000u
+#endif
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t hint_ns = MTL_WAIT_HINT_NS) {
   if (mbar_try_wait(bar, parity)) return;
   uint32_t polls = 0;
   uint64_t t0 = 0;
-  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+  while (!(hint_ns != 0 ? mbar_try_wait_hint(bar, parity, hint_ns) : mbar_try_wait(bar, parity))) {
     if ((++polls & 4095u) == 0) {
       const uint64_t now = globaltimer_ns();
       if (t0 == 0) t0 = now;

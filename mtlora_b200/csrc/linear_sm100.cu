@@ -43,7 +43,7 @@ __host__ __device__ inline SmemLayout smem_layout(int n_stages, int stage_bytes,
   l.usm = n_stages * stage_bytes;
   l.slabs = l.usm + n_uatoms * kTileABytes;
   l.bars = l.slabs + 8 * n_slabs * kSlabBytes;
-  l.total = l.bars + 512;
+  l.total = l.bars + 1024;
   return l;
 }
 
@@ -148,7 +148,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                   const __grid_constant__ CUtensorMap tm_down, const __grid_constant__ CUtensorMap tm_up,
                   const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_y2,
-                  const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ LinPlan p) {
+                  const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_in,
+                  const __grid_constant__ LinPlan p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -166,6 +167,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   auto p_empty = [&](int b) { return bar_base + 8u * (22 + b); };
   auto d_full = [&](int b) { return bar_base + 8u * (24 + b); };    // b = group * 2 + buffer
   auto d_empty = [&](int b) { return bar_base + 8u * (28 + b); };
+  auto in_bar = [&](int ew, int slab) { return bar_base + 8u * (40 + ew * 4 + slab); };  // epilogue-input slabs
   const uint32_t tmem_slot = bar_base + 8u * 32;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L.bars + 8u * 32);
 
@@ -199,6 +201,8 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       mbar_init(d_full(b), 1);
       mbar_init(d_empty(b), kEpiThreads / 2);
     }
+    for (int e = 0; e < 8; ++e)
+      for (int b = 0; b < 4; ++b) mbar_init(in_bar(e, b), 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -231,7 +235,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         for (int g = 0; g < p.n_groups; ++g) {
           const int len = p.grp_len[g];
           for (int kb = 0; kb < n_kb; ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_wait(empty_bar(stage), phase ^ 1u, p.wait_hint_ns);
             const uint32_t a_dst = smem_base + stage * stage_bytes;
             const uint32_t b_dst = a_dst + kTileABytes;
             mbar_arrive_expect_tx(full_bar(stage), kTileABytes + len * 128);
@@ -246,7 +250,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           const int c = it.split + ci * p.n_splits;
           for (int i = 0; i < p.n_main; ++i) {
             for (int kb = 0; kb < n_kb; ++kb) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);
+              mbar_wait(empty_bar(stage), phase ^ 1u, p.wait_hint_ns);
               const uint32_t a_dst = smem_base + stage * stage_bytes;
               const uint32_t b_dst = a_dst + kTileABytes;
               mbar_arrive_expect_tx(full_bar(stage), kTileABytes + p.BN * 128);
@@ -256,7 +260,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             }
           }
           for (int a = 0; a < n_uatoms; ++a) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_wait(empty_bar(stage), phase ^ 1u, p.wait_hint_ns);
             const uint32_t b_dst = smem_base + stage * stage_bytes + kTileABytes;
             mbar_arrive_expect_tx(full_bar(stage), p.BN * 128);
             tma_load_2d(b_dst, &tm_up, full_bar(stage), a * 64, c * p.BN);
@@ -286,7 +290,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           const uint32_t idesc = umma_idesc_bf16_m128(p.grp_len[g]);
           const uint32_t d_tmem = tmem_base + p.grp_r0[g];
           for (int kb = 0; kb < n_kb; ++kb) {
-            mbar_wait(full_bar(stage), phase);
+            mbar_wait(full_bar(stage), phase, p.wait_hint_ns);
             tc_fence_after();
             const uint32_t a_src = smem_base + stage * stage_bytes;
             const uint64_t adesc = umma_desc_sw128(a_src);
@@ -311,19 +315,19 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           uint32_t g0 = 0;
           if (multi) {
             const uint32_t pb = Cn % p.n_pbuf;
-            mbar_wait(p_empty(pb), ((Cn / p.n_pbuf) & 1u) ^ 1u);
+            mbar_wait(p_empty(pb), ((Cn / p.n_pbuf) & 1u) ^ 1u, p.wait_hint_ns);
             acc_dense = tmem_base + p_col0 + pb * p.BN;
           } else {
             const uint32_t k = G >> 1;
             g0 = (G & 1u) * 2 + k % p.n_dbuf;
-            mbar_wait(d_empty(g0), ((k / p.n_dbuf) & 1u) ^ 1u);
+            mbar_wait(d_empty(g0), ((k / p.n_dbuf) & 1u) ^ 1u, p.wait_hint_ns);
             acc_dense = tmem_base + d_col0 + ((G & 1u) * p.n_dbuf + k % p.n_dbuf) * p.BN;
           }
           tc_fence_after();
           bool first = true;
           for (int i = 0; i < p.n_main; ++i) {
             for (int kb = 0; kb < n_kb; ++kb) {
-              mbar_wait(full_bar(stage), phase);
+              mbar_wait(full_bar(stage), phase, p.wait_hint_ns);
               tc_fence_after();
               const uint32_t a_src = smem_base + stage * stage_bytes;
               const uint64_t adesc = umma_desc_sw128(a_src);
@@ -340,7 +344,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           if (multi) umma_commit(p_full(Cn % p.n_pbuf));
           if (n_uatoms > 0) {
             if (!u_waited) {
-              mbar_wait(u_ready, lw & 1u);
+              mbar_wait(u_ready, lw & 1u, p.wait_hint_ns);
               u_waited = true;
             }
             // the B_cat tiles of all rank atoms of this chunk occupy n_uatoms consecutive ring stages
@@ -349,7 +353,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               int s = stage;
               uint32_t ph = phase;
               for (int a = 0; a < n_uatoms; ++a) {
-                mbar_wait(full_bar(s), ph);
+                mbar_wait(full_bar(s), ph, p.wait_hint_ns);
                 st[a] = s;
                 if (++s == p.n_stages) {
                   s = 0;
@@ -366,7 +370,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               if (multi) {
                 const uint32_t k = G >> 1;
                 db = (G & 1u) * 2 + k % p.n_dbuf;
-                mbar_wait(d_empty(db), ((k / p.n_dbuf) & 1u) ^ 1u);
+                mbar_wait(d_empty(db), ((k / p.n_dbuf) & 1u) ^ 1u, p.wait_hint_ns);
                 tc_fence_after();
                 acc = tmem_base + d_col0 + ((G & 1u) * p.n_dbuf + k % p.n_dbuf) * p.BN;
                 started = false;
@@ -416,6 +420,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     uint8_t* slab_gen = smem_gen + L.slabs + ew * p.n_slabs * kSlabBytes;
     const uint32_t slab_base = smem_base + L.slabs + ew * p.n_slabs * kSlabBytes;
     int slab_k = 0;
+    uint32_t hc = 0;   // halves processed by this warp (slab rotation / input-barrier phase when has_in)
     const bool is_t0 = (warp == 4 && lane == 0);
     const uint32_t thr = dropout_threshold(p.drop_p);
     const float keep_scale = 1.f / (1.f - p.drop_p);
@@ -431,9 +436,9 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const int row0 = it.m0 + q4 * 32;
 
       if (p.R_pad > 0) {
-        mbar_wait(u_full, lw & 1u);
+        mbar_wait(u_full, lw & 1u, p.wait_hint_ns);
         tc_fence_after();
-        if (lw > 0) mbar_wait(usm_free, (lw - 1) & 1u);  // previous item's delta MMAs finished reading usm
+        if (lw > 0) mbar_wait(usm_free, (lw - 1) & 1u, p.wait_hint_ns);  // previous item's delta MMAs finished reading usm
         if (p.u_save != nullptr) {
           if (is_t0) bulk_wait_read<0>();                 // ... and so did its u_save bulk stores
           epi_bar_sync(1);
@@ -475,31 +480,38 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         for (int j = 0; j < n_items; ++j, ++G) {
           if ((G & 1u) != grp) continue;
           const uint32_t kk = G >> 1, dbuf = kk % p.n_dbuf, db = grp * 2 + dbuf;
-          // epilogue inputs that do not depend on the accumulators (GELU' argument, residual) are fetched one
-          // 16-column granule ahead; the first granule's loads are issued before waiting for the MMAs
+          // Epilogue inputs that do not depend on the accumulators (the GELU' argument of the fc2 backward, the residual
+          // of proj / fc2 forward) are staged by TMA into the very slab the half's output will be written to, one
+          // 64-column half ahead (across item and tile boundaries), so their HBM latency never stalls the math.
           constexpr bool need_aux = EP == LIN_EP_GELU_BWD, need_res = HAS_RES;
-          const size_t row_off = static_cast<size_t>(grow) * p.Nn;
-          const __nv_bfloat16* aux_row = need_aux ? p.aux + j * stream_stride + row_off : nullptr;
-          const __nv_bfloat16* res_row =
-              need_res ? p.res + (p.res_streams == 1 ? 0 : j * stream_stride) + row_off : nullptr;
-          uint4 na0 = make_uint4(0, 0, 0, 0), na1 = na0, nr0 = na0, nr1 = na0;
-          auto fetch_extra = [&](int n0) {
-            if (row_ok && n0 < p.Nn) {
-              if (need_aux) {
-                na0 = __ldg(reinterpret_cast<const uint4*>(aux_row + n0));
-                na1 = __ldg(reinterpret_cast<const uint4*>(aux_row + n0) + 1);
+          constexpr bool has_in = need_aux || need_res;
+          int nx_w = w, nx_ci = ci, nx_j = j;      // lookahead: this group's next item
+          bool nx_valid = true;
+          if (has_in) {
+            uint32_t g2 = G;
+            int nchunks = it.n_my_chunks;
+            do {
+              ++nx_j; ++g2;
+              if (nx_j == n_items) {
+                nx_j = 0;
+                if (++nx_ci == nchunks) {
+                  nx_ci = 0;
+                  nx_w += gridDim.x;
+                  if (nx_w >= n_work) { nx_valid = false; break; }
+                  nchunks = get_work(p, nx_w).n_my_chunks;
+                }
               }
-              if (need_res) {
-                nr0 = __ldg(reinterpret_cast<const uint4*>(res_row + n0));
-                nr1 = __ldg(reinterpret_cast<const uint4*>(res_row + n0) + 1);
-              }
-            }
+            } while ((g2 & 1u) != grp);
+          }
+          auto issue_in = [&](int slab, int col, int r0, int strm) {   // lane 0 only
+            mbar_arrive_expect_tx(in_bar(ew, slab), kSlabBytes);
+            tma_load_3d(slab_base + slab * kSlabBytes, &tm_in, in_bar(ew, slab), col, r0, need_res && p.res_streams == 1 ? 0 : strm);
           };
-          fetch_extra(c * p.BN);
-          mbar_wait(d_full(db), (kk / p.n_dbuf) & 1u);
+          if (has_in && hc == 0 && lane == 0) issue_in(0, c * p.BN, row0, j);   // very first half of this warp
+          mbar_wait(d_full(db), (kk / p.n_dbuf) & 1u, p.wait_hint_ns);
           const bool use_p = multi && p.out_useP[j];
           if (use_p && !p_waited) {
-            mbar_wait(p_full(pb), (Cn / p.n_pbuf) & 1u);
+            mbar_wait(p_full(pb), (Cn / p.n_pbuf) & 1u, p.wait_hint_ns);
             p_waited = true;
           }
           tc_fence_after();
@@ -513,12 +525,27 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             // slabs of this half: y -> ks_y, GELU(y) -> ks_y2. A slab is reused every n_slabs stores; with at most
             // n_slabs - n_out bulk groups still pending the ones that used these slabs have been read.
             constexpr int n_out = dual ? 2 : 1;
-            if (lane == 0) {
-              if (p.n_slabs - n_out >= 1) bulk_wait_read<1>(); else bulk_wait_read<0>();
-            }
-            __syncwarp();
             const int ks_y = slab_k;
             const int ks_y2 = (slab_k + 1) % p.n_slabs;
+            if (has_in) {
+              // next half of this warp: same item, or the first half of the group's next item
+              const int ks_n = (slab_k + 1) % p.n_slabs;
+              if (lane == 0) {
+                if (p.n_slabs >= 3) bulk_wait_read<1>(); else bulk_wait_read<0>();   // slab ks_n's last store was read
+                if (h + 1 < n_half) {
+                  issue_in(ks_n, col_h + 64, row0, j);
+                } else if (nx_valid) {
+                  const WorkItem ni = get_work(p, nx_w);
+                  issue_in(ks_n, (ni.split + nx_ci * p.n_splits) * p.BN, ni.m0 + q4 * 32, nx_j);
+                }
+              }
+              mbar_wait(in_bar(ew, ks_y), (hc / p.n_slabs) & 1u, p.wait_hint_ns);
+            } else {
+              if (lane == 0) {
+                if (p.n_slabs - n_out >= 1) bulk_wait_read<1>(); else bulk_wait_read<0>();
+              }
+            }
+            __syncwarp();
             uint8_t* sy = slab_gen + ks_y * kSlabBytes;
             uint8_t* sy2 = slab_gen + ks_y2 * kSlabBytes;
 #pragma unroll 1
@@ -555,11 +582,11 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] *= rs;
               }
-              {
-                const uint4 a0 = na0, a1 = na1, r0 = nr0, r1 = nr1;
-                fetch_extra(n0 + 16);   // next granule (crosses into the next 64-column half when gq == 3)
+              if (has_in) {
+                const uint4 a0 = *reinterpret_cast<const uint4*>(sy + sw128_offset(lane, gq * 16));
+                const uint4 a1 = *reinterpret_cast<const uint4*>(sy + sw128_offset(lane, gq * 16 + 8));
+                const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
                 if (need_aux) {
-                  const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
                     float d0, d1;
@@ -567,13 +594,11 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     v[2 * i] *= d0;
                     v[2 * i + 1] *= d1;
                   }
-                }
-                if (need_res) {
-                  const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                } else {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
-                    v[2 * i] += bf16lo_to_f32(rw[i]);
-                    v[2 * i + 1] += bf16hi_to_f32(rw[i]);
+                    v[2 * i] += bf16lo_to_f32(aw[i]);
+                    v[2 * i + 1] += bf16hi_to_f32(aw[i]);
                   }
                 }
               }
@@ -605,6 +630,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               }
             }
             slab_k = (slab_k + n_out) % p.n_slabs;
+            ++hc;
             if (dual && p.drop_mode == 1 && j == 0) {
               // D(m) of the shared stream (LoRA dropout of the consuming fc2, drawn with seed + 1): derived from the
               // bf16-rounded activation in the y2 slab so that it equals dropout(y2, seed + 1) exactly
@@ -806,7 +832,8 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
   p.n_work = m_tiles * p.n_splits;
 
   // ---- shared memory: store slabs + U operand + as many ring stages as fit ---------------------------------------
-  p.n_slabs = (p.ep_mode == LIN_EP_GELU_DUAL) ? 3 : 2;
+  const bool has_in = p.ep_mode == LIN_EP_GELU_BWD || p.res != nullptr;   // epilogue inputs staged through the slabs
+  p.n_slabs = (p.ep_mode == LIN_EP_GELU_DUAL || has_in) ? 3 : 2;
   const int min_stages = n_uatoms > 0 ? n_uatoms + 2 : 2;
   if (smem_layout(min_stages, stage_bytes, p.R_pad, p.n_slabs).total + 1024 > 227u * 1024) p.n_slabs = 2;
   p.n_stages = kMaxStages;
@@ -817,7 +844,7 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
   MTL_REQUIRE(smem_bytes <= 227 * 1024, "linear: shared memory %u exceeds 227 KiB", smem_bytes);
 
   // ---- tensor maps ---------------------------------------------------------------------------
-  CUtensorMap tm_x, tm_w, tm_down, tm_up, tm_y, tm_y2, tm_u;
+  CUtensorMap tm_x, tm_w, tm_down, tm_up, tm_y, tm_y2, tm_u, tm_in;
   if (int e = make_tmap(&tm_x, x, p.Kc, p.M, p.S_in, LIN_BK, LIN_BM)) return e;
   if (int e = make_tmap(&tm_w, wm, p.Kc, p.Nn, 0, LIN_BK, p.BN)) return e;
   if (p.R_pad > 0) {
@@ -839,9 +866,18 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
   } else {
     tm_u = tm_y;
   }
+  MTL_REQUIRE(!(p.ep_mode == LIN_EP_GELU_BWD && p.res != nullptr), "linear: GELU' epilogue cannot take a residual");
+  if (p.ep_mode == LIN_EP_GELU_BWD) {
+    MTL_REQUIRE(p.aux != nullptr, "linear: GELU' epilogue needs aux");
+    if (int e = make_tmap(&tm_in, p.aux, p.Nn, p.M, p.S_out, 64, 32)) return e;
+  } else if (p.res != nullptr) {
+    if (int e = make_tmap(&tm_in, p.res, p.Nn, p.M, p.res_streams, 64, 32)) return e;
+  } else {
+    tm_in = tm_y;
+  }
 
   using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
-                            LinPlan);
+                            CUtensorMap, LinPlan);
   static KernelFn kernels[3][2] = {
       {mtl_linear_kernel<LIN_EP_NONE, false>, mtl_linear_kernel<LIN_EP_NONE, true>},
       {mtl_linear_kernel<LIN_EP_GELU_DUAL, false>, mtl_linear_kernel<LIN_EP_GELU_DUAL, true>},
@@ -849,6 +885,7 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   static int max_ctas = -1;
+  static uint32_t wait_hint = 1000u;
   std::call_once(attr_once, []() {
     for (int a = 0; a < 3; ++a)
       for (int b = 0; b < 2; ++b) {
@@ -857,15 +894,18 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
       }
     const char* e = getenv("MTL_LINEAR_MAX_CTAS");  // debugging aid: 0 = one CTA per work item (non-persistent)
     max_ctas = e ? atoi(e) : -1;
+    const char* h = getenv("MTL_WAIT_HINT_NS");      // mbarrier.try_wait suspend-time hint (tuning aid)
+    if (h) wait_hint = static_cast<uint32_t>(atoi(h));
   });
   MTL_CHECK_CUDA(attr_err);
+  p.wait_hint_ns = wait_hint;
   MTL_REQUIRE(p.ep_mode >= 0 && p.ep_mode <= 2, "linear: unknown epilogue mode %d", p.ep_mode);
 
   int grid = p.n_work < n_sm ? p.n_work : n_sm;
   if (max_ctas == 0) grid = p.n_work;
   else if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   kernels[p.ep_mode][p.res != nullptr ? 1 : 0]<<<grid, kThreads, smem_bytes, stream>>>(tm_x, tm_w, tm_down, tm_up, tm_y,
-                                                                                      tm_y2, tm_u, p);
+                                                                                      tm_y2, tm_u, tm_in, p);
   note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
   return 0;
