@@ -132,6 +132,22 @@ __device__ __forceinline__ void gelu_grad_fast2(float x0, float x1, float& d0, f
 struct WorkItem {
   int m0, split, n_my_chunks;
 };
+// Debug timeline (MTL_LINEAR_TRACE=<file>): CTA 0 records (globaltimer, code) pairs per role.
+struct Tracer {
+  unsigned long long* buf;
+  int n;
+  __device__ __forceinline__ void init(unsigned long long* base, int role) {
+    buf = (base != nullptr && blockIdx.x == 0) ? base + role * 2048 : nullptr;
+    n = 0;
+  }
+  __device__ __forceinline__ void ev(unsigned long long code) {
+    if (buf != nullptr && n < 1023) {
+      buf[2 * n] = globaltimer_ns();
+      buf[2 * n + 1] = code;
+      ++n;
+    }
+  }
+};
 __device__ __forceinline__ WorkItem get_work(const LinPlan& p, int w) {
   WorkItem it;
   const int m_tile = w / p.n_splits;
@@ -229,8 +245,11 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           phase ^= 1u;
         }
       };
+      Tracer tr;
+      tr.init(p.trace, 0);
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         const WorkItem it = get_work(p, w);
+        tr.ev(1000000ull + w);
         // phase 1: rank-space ("down") products
         for (int g = 0; g < p.n_groups; ++g) {
           const int len = p.grp_len[g];
@@ -256,6 +275,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               mbar_arrive_expect_tx(full_bar(stage), kTileABytes + p.BN * 128);
               tma_load_3d(a_dst, &tm_x, full_bar(stage), kb * LIN_BK, it.m0, p.main_in[i]);
               tma_load_2d(b_dst, &tm_w, full_bar(stage), kb * LIN_BK, c * p.BN);
+              tr.ev(2000000ull + ci * 1000 + kb);
               advance();
             }
           }
@@ -282,8 +302,11 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         }
       };
       uint32_t lw = 0, Cn = 0, G = 0;  // local work / chunk / item counters (same sequence in the epilogue warps)
+      Tracer tr;
+      tr.init(p.trace, 1);
       for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++lw) {
         const WorkItem it = get_work(p, w);
+        tr.ev(1000000ull + w);
         // ---- phase 1: U[:, group] = X[in] . Down[group]^T (the U columns were drained before u_ready of the
         //      previous work item, which this thread has already waited for)
         for (int g = 0; g < p.n_groups; ++g) {
@@ -324,10 +347,12 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             acc_dense = tmem_base + d_col0 + ((G & 1u) * p.n_dbuf + k % p.n_dbuf) * p.BN;
           }
           tc_fence_after();
+          tr.ev(3000000ull + ci);   // accumulator acquired
           bool first = true;
           for (int i = 0; i < p.n_main; ++i) {
             for (int kb = 0; kb < n_kb; ++kb) {
               mbar_wait(full_bar(stage), phase, p.wait_hint_ns);
+              tr.ev(2000000ull + ci * 1000 + kb);
               tc_fence_after();
               const uint32_t a_src = smem_base + stage * stage_bytes;
               const uint64_t adesc = umma_desc_sw128(a_src);
@@ -399,6 +424,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               advance();
             }
           }
+          tr.ev(4000000ull + ci);   // chunk issued
           if (multi) {
             ++Cn;
           } else {
@@ -428,8 +454,11 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     constexpr bool dual = EP == LIN_EP_GELU_DUAL;
 
     uint32_t lw = 0, Cn = 0, G = 0;
+    Tracer tr;
+    tr.init((lane == 0 && q4 == 0) ? p.trace : nullptr, 2 + static_cast<int>(grp));
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++lw) {
       const WorkItem it = get_work(p, w);
+      tr.ev(1000000ull + w);
       const int grow = it.m0 + row;
       const bool row_ok = grow < p.M;
       const int sample = (p.rows_per_sample > 0) ? min(grow / p.rows_per_sample, p.n_samples - 1) : 0;
@@ -458,6 +487,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           *reinterpret_cast<uint4*>(atom + sw128_offset(row, c0)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           *reinterpret_cast<uint4*>(atom + sw128_offset(row, c0 + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
+        tr.ev(8000000ull);   // U converted
         fence_proxy_async_smem();
         tc_fence_before();
         if (p.u_save != nullptr && it.split == 0) {
@@ -508,7 +538,9 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             tma_load_3d(slab_base + slab * kSlabBytes, &tm_in, in_bar(ew, slab), col, r0, need_res && p.res_streams == 1 ? 0 : strm);
           };
           if (has_in && hc == 0 && lane == 0) issue_in(0, c * p.BN, row0, j);   // very first half of this warp
+          tr.ev(5000000ull + ci * 10 + j);   // waiting for accumulator
           mbar_wait(d_full(db), (kk / p.n_dbuf) & 1u, p.wait_hint_ns);
+          tr.ev(6000000ull + ci * 10 + j);   // got it
           const bool use_p = multi && p.out_useP[j];
           if (use_p && !p_waited) {
             mbar_wait(p_full(pb), (Cn / p.n_pbuf) & 1u, p.wait_hint_ns);
@@ -668,6 +700,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           }
           tc_fence_before();
           mbar_arrive(d_empty(db));
+          tr.ev(7000000ull + ci * 10 + j);   // item done
         }
         if (multi) {
           tc_fence_before();
@@ -753,17 +786,19 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
   p.n_dbuf = 2;
   int bn = 64;
   if (!multi) {
-    if (heavy && p.Nn > 64) {
+    // one accumulator per item: wide chunks amortise the per-chunk cost of the single MMA-issuing thread
+    // (~100 ns per tcgen05 op, measured) and the X-tile re-reads; the two groups alternate items
+    if (p.Nn > 64) {
       p.n_dbuf = 1;
       bn = (p.Nn > 128 && u_cols + 2 * 192 <= 512) ? 192 : 128;
       if (u_cols + 2 * bn > 512) bn = 64;
-    } else if (u_cols == 0 && p.Nn > 64) {
-      bn = 128;
     }
     if (u_cols + 2 * p.n_dbuf * bn > 512) p.n_dbuf = 1;
   } else {
     p.n_pbuf = 2;
-    if (heavy && p.Nn > 64 && u_cols + 3 * 128 <= 512) {
+    // A single output stream in split mode (the dropout-masked adapter term of the backward) alternates its chunks
+    // between the two epilogue groups: both need their own P and D, so keep narrow chunks with double buffering.
+    if (heavy && p.S_out > 1 && p.Nn > 64 && u_cols + 3 * 128 <= 512) {
       bn = 128;
       p.n_pbuf = 1;
       p.n_dbuf = 1;
@@ -771,6 +806,13 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
     if (u_cols + (p.n_pbuf + 2 * p.n_dbuf) * bn > 512) p.n_pbuf = 1;
     if (u_cols + (p.n_pbuf + 2 * p.n_dbuf) * bn > 512) { p.n_pbuf = 2; p.n_dbuf = 1; }
     if (u_cols + (p.n_pbuf + 2 * p.n_dbuf) * bn > 512) p.n_pbuf = 1;
+  }
+  if (const char* e = getenv("MTL_LINEAR_BN")) {   // tuning aid: force the chunk width (merged mode only)
+    const int fb = atoi(e);
+    if (!multi && (fb == 64 || fb == 128 || fb == 192) && u_cols + 2 * fb <= 512) {
+      bn = fb;
+      p.n_dbuf = (u_cols + 4 * fb <= 512) ? 2 : 1;
+    }
   }
   p.BN = bn;
   p.n_chunks = (p.Nn + bn - 1) / bn;
@@ -828,6 +870,10 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
         p.n_splits = sp;
       }
     }
+  }
+  if (const char* e = getenv("MTL_LINEAR_SPLITS")) {
+    const int fs = atoi(e);
+    if (fs >= 1 && fs <= p.n_chunks) p.n_splits = fs;
   }
   p.n_work = m_tiles * p.n_splits;
 
@@ -899,6 +945,12 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
   });
   MTL_CHECK_CUDA(attr_err);
   p.wait_hint_ns = wait_hint;
+  static const char* trace_path = getenv("MTL_LINEAR_TRACE");
+  p.trace = nullptr;
+  if (trace_path != nullptr) {
+    MTL_CHECK_CUDA(cudaMalloc(&p.trace, 4 * 2048 * sizeof(unsigned long long)));
+    MTL_CHECK_CUDA(cudaMemsetAsync(p.trace, 0, 4 * 2048 * sizeof(unsigned long long), stream));
+  }
   MTL_REQUIRE(p.ep_mode >= 0 && p.ep_mode <= 2, "linear: unknown epilogue mode %d", p.ep_mode);
 
   int grid = p.n_work < n_sm ? p.n_work : n_sm;
@@ -908,6 +960,20 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
                                                                                       tm_y2, tm_u, tm_in, p);
   note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
+  if (p.trace != nullptr) {   // debugging only: synchronous dump of CTA 0's timeline (last launch wins)
+    static unsigned long long host[4 * 2048];
+    MTL_CHECK_CUDA(cudaStreamSynchronize(stream));
+    MTL_CHECK_CUDA(cudaMemcpy(host, p.trace, sizeof(host), cudaMemcpyDeviceToHost));
+    cudaFree(p.trace);
+    if (FILE* f = fopen(trace_path, "w")) {
+      fprintf(f, "# M=%d K=%d N=%d BN=%d chunks=%d splits=%d stages=%d slabs=%d pbuf=%d dbuf=%d multi=%d\n", p.M, p.Kc, p.Nn,
+              p.BN, p.n_chunks, p.n_splits, p.n_stages, p.n_slabs, p.n_pbuf, p.n_dbuf, p.n_regions > 1);
+      for (int r = 0; r < 4; ++r)
+        for (int i = 0; i < 1024 && host[r * 2048 + 2 * i] != 0; ++i)
+          fprintf(f, "%d %llu %llu\n", r, host[r * 2048 + 2 * i], host[r * 2048 + 2 * i + 1]);
+      fclose(f);
+    }
+  }
   return 0;
 }
 

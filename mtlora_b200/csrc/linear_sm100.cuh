@@ -76,6 +76,7 @@ struct LinPlan {
   int drop_mode;
   float drop_p;
   uint64_t drop_seed;
+  unsigned long long* trace;  // debug timeline of CTA 0 (MTL_LINEAR_TRACE), else null: [role][1024] (time, code) pairs
   uint32_t wait_hint_ns;  // mbarrier.try_wait suspend-time hint used by every role's waits
   int force_split;  // keep dense and adapter accumulators in separate TMEM regions even if S_out == 1
 };
