@@ -11,8 +11,9 @@
 //     (chunk, stream): TMEM -> registers -> bias / DropPath scale / GELU / residual -> bf16 -> swizzled smem slab ->
 //     TMA store, so every output element is written exactly once by coalesced bulk stores.
 //
-// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4-7 = epilogue group 0, warps 8-11 = epilogue group 1 (warp % 4 = TMEM lane quadrant).
+// Warp roles (128 + 128 * kGroups threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4.. = epilogue groups of 4 warps (warp % 4 = TMEM lane quadrant). kGroups = 2: a third group was measured
+// slower (it costs the third store slab, the second accumulator per group and the 128-column chunks).
 #include "linear_sm100.cuh"
 
 #include <cudaTypedefs.h>
@@ -23,8 +24,10 @@ namespace mtl {
 
 namespace {
 
-constexpr int kThreads = 384;
-constexpr int kEpiThreads = 256;
+constexpr int kGroups = 2;                        // epilogue warp-groups (4 warps each: one per TMEM lane quadrant)
+constexpr int kEpiWarps = 4 * kGroups;
+constexpr int kThreads = 128 + 32 * kEpiWarps;   // 4 control warps + epilogue warps
+constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kTileABytes = LIN_BM * LIN_BK * 2;  // 16 KiB: one [128 x 64] bf16 K-major SW128 tile
 constexpr int kSlabBytes = 32 * 64 * 2;           // 4 KiB: one warp's [32 rows x 64 cols] bf16 store slab
 constexpr int kMaxStages = 8;
@@ -42,7 +45,7 @@ __host__ __device__ inline SmemLayout smem_layout(int n_stages, int stage_bytes,
   const uint32_t n_uatoms = (r_pad + 63) / 64;
   l.usm = n_stages * stage_bytes;
   l.slabs = l.usm + n_uatoms * kTileABytes;
-  l.bars = l.slabs + 8 * n_slabs * kSlabBytes;
+  l.bars = l.slabs + kEpiWarps * n_slabs * kSlabBytes;
   l.total = l.bars + 1024;
   return l;
 }
@@ -100,33 +103,66 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
 // 0.5 * erf(x / sqrt 2) on |x| <= 4.25 (max abs error 1.1e-5, far below the bf16 resolution of the outputs); the
 // argument is clamped, so Phi saturates at 1 - 1e-5 / 1e-5. nn.GELU() is the exact-erf GELU (reference :45):
 // GELU(x) = x * Phi(x), GELU'(x) = Phi(x) + x * phi(x). Two elements per instruction.
-__device__ __forceinline__ uint64_t phi2(float x0, float x1) {
-  const uint64_t xc = pack2(fminf(fmaxf(x0, -4.25f), 4.25f), fminf(fmaxf(x1, -4.25f), 4.25f));
-  const uint64_t t = mul2(xc, xc);
-  uint64_t q = MTL_C2(5.565109802e-11f);
-  q = fma2(q, t, MTL_C2(-5.327931323e-09f));
-  q = fma2(q, t, MTL_C2(2.255476184e-07f));
-  q = fma2(q, t, MTL_C2(-5.626496851e-06f));
-  q = fma2(q, t, MTL_C2(9.341922331e-05f));
-  q = fma2(q, t, MTL_C2(-1.108562514e-03f));
-  q = fma2(q, t, MTL_C2(9.815966060e-03f));
-  q = fma2(q, t, MTL_C2(-6.634444852e-02f));
-  q = fma2(q, t, MTL_C2(3.989024332e-01f));
-  return fma2(xc, q, MTL_C2(0.5f));
-}
-__device__ __forceinline__ void gelu_fast2(float x0, float x1, float& g0, float& g1) {
-  unpack2(mul2(pack2(x0, x1), phi2(x0, x1)), g0, g1);
+// Evaluated breadth-first over the 8 element pairs of a 16-column granule so that every Horner step issues 8
+// independent FFMA2 (the epilogue runs with only two warps per scheduler: dependent chains would stall the issue port).
+__device__ __forceinline__ void phi16(const float (&v)[16], uint64_t (&phi)[8]) {
+  uint64_t xc[8], t[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    xc[i] = pack2(fminf(fmaxf(v[2 * i], -4.25f), 4.25f), fminf(fmaxf(v[2 * i + 1], -4.25f), 4.25f));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t[i] = mul2(xc[i], xc[i]);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) q[i] = fma2(MTL_C2(5.565109802e-11f), t[i], MTL_C2(-5.327931323e-09f));
+#define MTL_HORNER(C)              \
+  _Pragma("unroll") for (int i = 0; i < 8; ++i) q[i] = fma2(q[i], t[i], MTL_C2(C));
+  MTL_HORNER(2.255476184e-07f)
+  MTL_HORNER(-5.626496851e-06f)
+  MTL_HORNER(9.341922331e-05f)
+  MTL_HORNER(-1.108562514e-03f)
+  MTL_HORNER(9.815966060e-03f)
+  MTL_HORNER(-6.634444852e-02f)
+  MTL_HORNER(3.989024332e-01f)
+#undef MTL_HORNER
+#pragma unroll
+  for (int i = 0; i < 8; ++i) phi[i] = fma2(xc[i], q[i], MTL_C2(0.5f));
 }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void gelu_grad_fast2(float x0, float x1, float& d0, float& d1) {
-  // pdf = exp(-x^2 / 2) / sqrt(2 pi)
-  const float p0 = 0.39894228040143267794f * ex2_approx(-0.72134752044448170368f * x0 * x0);
-  const float p1 = 0.39894228040143267794f * ex2_approx(-0.72134752044448170368f * x1 * x1);
-  unpack2(fma2(pack2(x0, x1), pack2(p0, p1), phi2(x0, x1)), d0, d1);
+// GELU(v) for a granule, packed to bf16x2
+__device__ __forceinline__ void gelu16_pack(const float (&v)[16], uint32_t (&pk)[8]) {
+  uint64_t phi[8];
+  phi16(v, phi);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float g0, g1;
+    unpack2(mul2(pack2(v[2 * i], v[2 * i + 1]), phi[i]), g0, g1);
+    pk[i] = pack_bf16x2(g0, g1);
+  }
+}
+// v *= GELU'(a) for a granule; a given as 8 packed bf16x2 words. GELU'(x) = Phi(x) + x * pdf(x)
+__device__ __forceinline__ void gelu_grad16_mul(float (&v)[16], const uint32_t (&aw)[8]) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[2 * i] = bf16lo_to_f32(aw[i]);
+    a[2 * i + 1] = bf16hi_to_f32(aw[i]);
+  }
+  uint64_t phi[8];
+  phi16(a, phi);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    // pdf = exp(-x^2 / 2) / sqrt(2 pi)
+    const float p0 = 0.39894228040143267794f * ex2_approx(-0.72134752044448170368f * a[2 * i] * a[2 * i]);
+    const float p1 = 0.39894228040143267794f * ex2_approx(-0.72134752044448170368f * a[2 * i + 1] * a[2 * i + 1]);
+    float d0, d1;
+    unpack2(fma2(pack2(a[2 * i], a[2 * i + 1]), pack2(p0, p1), phi[i]), d0, d1);
+    v[2 * i] *= d0;
+    v[2 * i + 1] *= d1;
+  }
 }
 
 struct WorkItem {
@@ -182,10 +218,10 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   auto p_full = [&](int b) { return bar_base + 8u * (20 + b); };
   auto p_empty = [&](int b) { return bar_base + 8u * (22 + b); };
   auto d_full = [&](int b) { return bar_base + 8u * (24 + b); };    // b = group * 2 + buffer
-  auto d_empty = [&](int b) { return bar_base + 8u * (28 + b); };
-  auto in_bar = [&](int ew, int slab) { return bar_base + 8u * (40 + ew * 4 + slab); };  // epilogue-input slabs
-  const uint32_t tmem_slot = bar_base + 8u * 32;
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L.bars + 8u * 32);
+  auto d_empty = [&](int b) { return bar_base + 8u * (32 + b); };
+  auto in_bar = [&](int ew, int slab) { return bar_base + 8u * (48 + ew * 4 + slab); };  // epilogue-input slabs
+  const uint32_t tmem_slot = bar_base + 8u * 40;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L.bars + 8u * 40);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -213,11 +249,11 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       mbar_init(p_full(b), 1);
       mbar_init(p_empty(b), kEpiThreads);
     }
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < 2 * kGroups; ++b) {
       mbar_init(d_full(b), 1);
-      mbar_init(d_empty(b), kEpiThreads / 2);
+      mbar_init(d_empty(b), 128);
     }
-    for (int e = 0; e < 8; ++e)
+    for (int e = 0; e < kEpiWarps; ++e)
       for (int b = 0; b < 4; ++b) mbar_init(in_bar(e, b), 1);
     mbar_fence_init();
   }
@@ -230,7 +266,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
   // TMEM columns: [0, u_cols) rank-space accumulators U; then P[n_pbuf] (multi); then D[group][n_dbuf]
-  // item G -> group G & 1, that group's k-th item (k = G >> 1) -> buffer k % n_dbuf, use k / n_dbuf
+  // item G -> group G % kGroups, that group's k-th item (k = G / kGroups) -> buffer k % n_dbuf, use k / n_dbuf
   const uint32_t p_col0 = p.acc_col0;
   const uint32_t d_col0 = p.acc_col0 + (multi ? p.n_pbuf * p.BN : 0);
 
@@ -341,10 +377,10 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             mbar_wait(p_empty(pb), ((Cn / p.n_pbuf) & 1u) ^ 1u, p.wait_hint_ns);
             acc_dense = tmem_base + p_col0 + pb * p.BN;
           } else {
-            const uint32_t k = G >> 1;
-            g0 = (G & 1u) * 2 + k % p.n_dbuf;
+            const uint32_t k = G / kGroups;
+            g0 = (G % kGroups) * 2 + k % p.n_dbuf;
             mbar_wait(d_empty(g0), ((k / p.n_dbuf) & 1u) ^ 1u, p.wait_hint_ns);
-            acc_dense = tmem_base + d_col0 + ((G & 1u) * p.n_dbuf + k % p.n_dbuf) * p.BN;
+            acc_dense = tmem_base + d_col0 + ((G % kGroups) * p.n_dbuf + k % p.n_dbuf) * p.BN;
           }
           tc_fence_after();
           tr.ev(3000000ull + ci);   // accumulator acquired
@@ -393,11 +429,11 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               bool started;
               uint32_t db = 0;
               if (multi) {
-                const uint32_t k = G >> 1;
-                db = (G & 1u) * 2 + k % p.n_dbuf;
+                const uint32_t k = G / kGroups;
+                db = (G % kGroups) * 2 + k % p.n_dbuf;
                 mbar_wait(d_empty(db), ((k / p.n_dbuf) & 1u) ^ 1u, p.wait_hint_ns);
                 tc_fence_after();
-                acc = tmem_base + d_col0 + ((G & 1u) * p.n_dbuf + k % p.n_dbuf) * p.BN;
+                acc = tmem_base + d_col0 + ((G % kGroups) * p.n_dbuf + k % p.n_dbuf) * p.BN;
                 started = false;
               } else {
                 acc = acc_dense;
@@ -439,7 +475,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   } else if (warp >= 4) {
     // ======================================= U converter + epilogue =======================================
     const int q4 = warp & 3;                 // TMEM lane quadrant
-    const uint32_t grp = (warp - 4) >> 2;    // epilogue group 0 / 1
+    const uint32_t grp = (warp - 4) >> 2;    // epilogue group 0 .. kGroups-1
     const int ew = warp - 4;                 // 0..7
     const int row = q4 * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
@@ -472,7 +508,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           if (is_t0) bulk_wait_read<0>();                 // ... and so did its u_save bulk stores
           epi_bar_sync(1);
         }
-        for (int gq = static_cast<int>(grp); gq < p.R_pad / 16; gq += 2) {
+        for (int gq = static_cast<int>(grp); gq < p.R_pad / 16; gq += kGroups) {
           uint32_t r[16];
           tmem_ld16(t_lane + gq * 16, r);
           tmem_ld_wait();
@@ -508,8 +544,8 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const uint32_t pb = multi ? (Cn % p.n_pbuf) : 0;
         bool p_waited = false;
         for (int j = 0; j < n_items; ++j, ++G) {
-          if ((G & 1u) != grp) continue;
-          const uint32_t kk = G >> 1, dbuf = kk % p.n_dbuf, db = grp * 2 + dbuf;
+          if ((G % kGroups) != grp) continue;
+          const uint32_t kk = G / kGroups, dbuf = kk % p.n_dbuf, db = grp * 2 + dbuf;
           // Epilogue inputs that do not depend on the accumulators (the GELU' argument of the fc2 backward, the residual
           // of proj / fc2 forward) are staged by TMA into the very slab the half's output will be written to, one
           // 64-column half ahead (across item and tile boundaries), so their HBM latency never stalls the math.
@@ -531,7 +567,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                   nchunks = get_work(p, nx_w).n_my_chunks;
                 }
               }
-            } while ((g2 & 1u) != grp);
+            } while ((g2 % kGroups) != grp);
           }
           auto issue_in = [&](int slab, int col, int r0, int strm) {   // lane 0 only
             mbar_arrive_expect_tx(in_bar(ew, slab), kSlabBytes);
@@ -580,7 +616,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             __syncwarp();
             uint8_t* sy = slab_gen + ks_y * kSlabBytes;
             uint8_t* sy2 = slab_gen + ks_y2 * kSlabBytes;
-#pragma unroll 1
+#pragma unroll 2
             for (int gq = 0; gq < 4; ++gq) {
               const int n0 = col_h + gq * 16;
               if (n0 >= p.Nn) break;
@@ -619,13 +655,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 const uint4 a1 = *reinterpret_cast<const uint4*>(sy + sw128_offset(lane, gq * 16 + 8));
                 const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
                 if (need_aux) {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    float d0, d1;
-                    gelu_grad_fast2(bf16lo_to_f32(aw[i]), bf16hi_to_f32(aw[i]), d0, d1);
-                    v[2 * i] *= d0;
-                    v[2 * i + 1] *= d1;
-                  }
+                  gelu_grad16_mul(v, aw);
                 } else {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
@@ -640,12 +670,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               *reinterpret_cast<uint4*>(sy + sw128_offset(lane, gq * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               *reinterpret_cast<uint4*>(sy + sw128_offset(lane, gq * 16 + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
               if (dual) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  float g0v, g1v;
-                  gelu_fast2(v[2 * i], v[2 * i + 1], g0v, g1v);
-                  pk[i] = pack_bf16x2(g0v, g1v);
-                }
+                gelu16_pack(v, pk);
                 *reinterpret_cast<uint4*>(sy2 + sw128_offset(lane, gq * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 *reinterpret_cast<uint4*>(sy2 + sw128_offset(lane, gq * 16 + 8)) =
                     make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -782,42 +807,48 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
   // bound: narrow chunks, two accumulators per epilogue group so the MMA warp runs ahead. Long contractions are
   // bound by operand traffic (every chunk re-streams the X tile from L2): wide chunks, one accumulator per group.
   const bool heavy = p.Kc >= 256;
+  // TMEM columns = u_cols + n_pbuf * BN (multi) + kGroups * n_dbuf * BN <= 512.
+  auto cols = [&](int bn_, int pb, int db) { return u_cols + (pb + kGroups * db) * bn_; };
+  const int n_uatoms = (p.R_pad + 63) / 64;
+  MTL_REQUIRE(n_uatoms <= kMaxUAtoms, "linear: too many rank atoms");
+  const int min_stages = n_uatoms > 0 ? n_uatoms + 2 : 2;
+  // epilogues with two outputs per half (GELU pair) or with TMA-staged inputs want a third store slab per warp:
+  // with two, every half waits for the bulk store that just left (measured: 12.7 us instead of ~5 us per item)
+  const int want_slabs = (p.ep_mode == LIN_EP_GELU_DUAL || p.ep_mode == LIN_EP_GELU_BWD || p.res != nullptr) ? 3 : 2;
+  auto fits_smem = [&](int bn_, int slabs) {   // with the minimum ring depth
+    return smem_layout(min_stages, kTileABytes + bn_ * 128, p.R_pad, slabs).total + 1024 <= 227u * 1024;
+  };
   p.n_pbuf = 0;
-  p.n_dbuf = 2;
+  p.n_dbuf = 1;
   int bn = 64;
   if (!multi) {
     // one accumulator per item: wide chunks amortise the per-chunk cost of the single MMA-issuing thread
-    // (~100 ns per tcgen05 op, measured) and the X-tile re-reads; the two groups alternate items
-    if (p.Nn > 64) {
-      p.n_dbuf = 1;
-      bn = (p.Nn > 128 && u_cols + 2 * 192 <= 512) ? 192 : 128;
-      if (u_cols + 2 * bn > 512) bn = 64;
-    }
-    if (u_cols + 2 * p.n_dbuf * bn > 512) p.n_dbuf = 1;
+    // (~100 ns per tcgen05 op, measured) and the X-tile re-reads; the groups take the items round-robin
+    if (p.Nn > 64 && cols(128, 0, 1) <= 512 && fits_smem(128, want_slabs)) bn = 128;
+    if (p.Nn > 128 && cols(192, 0, 1) <= 512 && fits_smem(192, want_slabs)) bn = 192;
+    if (cols(bn, 0, 2) <= 512) p.n_dbuf = 2;
   } else {
+    // dense accumulator P per chunk + delta accumulators per group
     p.n_pbuf = 2;
-    // A single output stream in split mode (the dropout-masked adapter term of the backward) alternates its chunks
-    // between the two epilogue groups: both need their own P and D, so keep narrow chunks with double buffering.
-    if (heavy && p.S_out > 1 && p.Nn > 64 && u_cols + 3 * 128 <= 512) {
+    // (measured: for long contractions 128-column chunks with two slabs beat 64-column chunks with three)
+    if (heavy && p.S_out > 1 && p.Nn > 64 && cols(128, 1, 1) <= 512 && fits_smem(128, 2)) {
       bn = 128;
       p.n_pbuf = 1;
-      p.n_dbuf = 1;
     }
-    if (u_cols + (p.n_pbuf + 2 * p.n_dbuf) * bn > 512) p.n_pbuf = 1;
-    if (u_cols + (p.n_pbuf + 2 * p.n_dbuf) * bn > 512) { p.n_pbuf = 2; p.n_dbuf = 1; }
-    if (u_cols + (p.n_pbuf + 2 * p.n_dbuf) * bn > 512) p.n_pbuf = 1;
+    if (cols(bn, p.n_pbuf, 1) > 512) p.n_pbuf = 1;
+    if (cols(bn, p.n_pbuf, 2) <= 512) p.n_dbuf = 2;
   }
   if (const char* e = getenv("MTL_LINEAR_BN")) {   // tuning aid: force the chunk width (merged mode only)
     const int fb = atoi(e);
-    if (!multi && (fb == 64 || fb == 128 || fb == 192) && u_cols + 2 * fb <= 512) {
+    if (!multi && (fb == 64 || fb == 128 || fb == 192) && cols(fb, 0, 1) <= 512) {
       bn = fb;
-      p.n_dbuf = (u_cols + 4 * fb <= 512) ? 2 : 1;
+      p.n_dbuf = cols(fb, 0, 2) <= 512 ? 2 : 1;
     }
   }
   p.BN = bn;
   p.n_chunks = (p.Nn + bn - 1) / bn;
   p.acc_col0 = u_cols;
-  const int need_cols = u_cols + (p.n_pbuf + 2 * p.n_dbuf) * bn;
+  const int need_cols = cols(bn, p.n_pbuf, p.n_dbuf);
   MTL_REQUIRE(need_cols <= 512, "linear: TMEM budget exceeded (R_pad=%d, S_out=%d)", p.R_pad, p.S_out);
   p.tmem_cols = 32;
   while (p.tmem_cols < need_cols) p.tmem_cols *= 2;
@@ -845,8 +876,6 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
   }
   p.stage_b_bytes = bn * 128;
   const int stage_bytes = kTileABytes + p.stage_b_bytes;
-  const int n_uatoms = (p.R_pad + 63) / 64;
-  MTL_REQUIRE(n_uatoms <= kMaxUAtoms, "linear: too many rank atoms");
 
   // ---- work decomposition: (128-row tile, column split), persistent CTAs ---------------------------------------
   const int m_tiles = (p.M + LIN_BM - 1) / LIN_BM;
@@ -879,8 +908,7 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
 
   // ---- shared memory: store slabs + U operand + as many ring stages as fit ---------------------------------------
   const bool has_in = p.ep_mode == LIN_EP_GELU_BWD || p.res != nullptr;   // epilogue inputs staged through the slabs
-  p.n_slabs = (p.ep_mode == LIN_EP_GELU_DUAL || has_in) ? 3 : 2;
-  const int min_stages = n_uatoms > 0 ? n_uatoms + 2 : 2;
+  p.n_slabs = (p.ep_mode == LIN_EP_GELU_DUAL || has_in) ? 3 : 2;   // reduced to 2 below when smem is short
   if (smem_layout(min_stages, stage_bytes, p.R_pad, p.n_slabs).total + 1024 > 227u * 1024) p.n_slabs = 2;
   p.n_stages = kMaxStages;
   while (p.n_stages > min_stages &&

@@ -12,7 +12,8 @@ namespace mtl {
 
 namespace {
 
-constexpr int TA = 64, TB = 64, TM = 32;
+constexpr int TA = 64, TB = 64, TM = 64;
+constexpr int kChunks = TM * 8 / 128;   // 16-byte chunks of P (and of Q) each thread stages per step
 constexpr int LDS = 72;  // smem row stride (bf16): 144 B, conflict-free for ldmatrix
 
 struct XtyParams {
@@ -54,11 +55,11 @@ __global__ void __launch_bounds__(128) xty_kernel(const XtyParams p) {
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
 
-  // each thread stages 2 chunks of P and 2 of Q per step: chunk id = tid + 128*i -> row = id / 8, col8 = id % 8
-  uint4 rp[2], rq[2];
+  // each thread stages kChunks chunks of P and of Q per step: chunk id = tid + 128*i -> row = id / 8, col8 = id % 8
+  uint4 rp[kChunks], rq[kChunks];
   auto fetch = [&](long m0) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kChunks; ++i) {
       const int id = threadIdx.x + 128 * i;
       const int r = id >> 3, c8 = (id & 7) * 8;
       rp[i] = load_chunk(p.P, p.ldp, m0 + r, m_end, a0 + c8, p.a);
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(128) xty_kernel(const XtyParams p) {
   for (long m0 = m_begin; m0 < m_end; m0 += TM) {
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kChunks; ++i) {
       const int id = threadIdx.x + 128 * i;
       const int r = id >> 3, c8 = (id & 7) * 8;
       *reinterpret_cast<uint4*>(Ps + r * LDS + c8) = rp[i];
