@@ -263,6 +263,13 @@ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t col_bf16
   return (row >> 3) * 1024u + (row & 7u) * 128u + chunk * 16u + (col_bf16 & 7u) * 2u;
 }
 
+// Byte offset of element (row, col) inside a SWIZZLE_64B tile whose rows are 32 bf16 wide (64 bytes); the tile base
+// must be 512-byte aligned. Swizzle<2,4,3>: the 16-byte chunk index is XORed with bits 7-8 of the byte address.
+__device__ __forceinline__ uint32_t sw64_offset(uint32_t row, uint32_t col_bf16) {
+  const uint32_t chunk = (col_bf16 >> 3) ^ ((row >> 1) & 3u);
+  return row * 64u + chunk * 16u + (col_bf16 & 7u) * 2u;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Legacy tensor path helpers (mma.sync m16n8k16 bf16) for the small attention / reduction kernels
 // ---------------------------------------------------------------------------------------------

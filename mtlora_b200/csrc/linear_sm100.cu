@@ -24,12 +24,22 @@ namespace mtl {
 
 namespace {
 
-constexpr int kGroups = 2;                        // epilogue warp-groups (4 warps each: one per TMEM lane quadrant)
-constexpr int kEpiWarps = 4 * kGroups;
+constexpr int kGroups = 2;                        // epilogue groups: each owns one accumulator item at a time
+constexpr int kColSplit = 2;                      // warps per TMEM lane quadrant inside a group: each takes 32 of the
+                                                  // 64 columns of a half (the epilogue is latency-bound per warp, so
+                                                  // 4 warps per scheduler instead of 2 nearly halve the item time)
+constexpr int kGroupWarps = 4 * kColSplit;
+constexpr int kEpiWarps = kGroupWarps * kGroups;
 constexpr int kThreads = 128 + 32 * kEpiWarps;   // 4 control warps + epilogue warps
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kTileABytes = LIN_BM * LIN_BK * 2;  // 16 KiB: one [128 x 64] bf16 K-major SW128 tile
-constexpr int kSlabBytes = 32 * 64 * 2;           // 4 KiB: one warp's [32 rows x 64 cols] bf16 store slab
+constexpr int kPieceCols = 64 / kColSplit;        // columns of a half one warp converts and stores
+constexpr int kPieceGran = kPieceCols / 16;
+constexpr int kSlabBytes = 32 * kPieceCols * 2;   // 2 KiB: one warp's [32 rows x 32 cols] bf16 store slab (SW64)
+// launch: 640 threads x 96 registers; the control warpgroup drops to kCtrlRegs, the epilogue warpgroups grow to kEpiRegs
+constexpr int kCtrlRegs = 64, kEpiRegs = 104;
+static_assert(128 * kCtrlRegs + kEpiThreads * kEpiRegs <= kThreads * 96, "register pool of the CTA exceeded");
+static_assert(kColSplit == 2, "slab swizzle / tensor-map boxes are written for 32-column pieces");
 constexpr int kMaxStages = 8;
 constexpr int kMaxUAtoms = LIN_MAX_GRAN / 4;
 
@@ -251,7 +261,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     }
     for (int b = 0; b < 2 * kGroups; ++b) {
       mbar_init(d_full(b), 1);
-      mbar_init(d_empty(b), 128);
+      mbar_init(d_empty(b), 32 * kGroupWarps);
     }
     for (int e = 0; e < kEpiWarps; ++e)
       for (int b = 0; b < 4; ++b) mbar_init(in_bar(e, b), 1);
@@ -270,6 +280,9 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   const uint32_t p_col0 = p.acc_col0;
   const uint32_t d_col0 = p.acc_col0 + (multi ? p.n_pbuf * p.BN : 0);
 
+  // Register rebalancing: the 4 control warps (one warpgroup) need few registers, the epilogue warps many.
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtrlRegs));
   if (warp == 0) {
     // ============================================ TMA producer ============================================
     if (lane == 0) {
@@ -472,11 +485,14 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  }
+  } else {
     // ======================================= U converter + epilogue =======================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     const int q4 = warp & 3;                 // TMEM lane quadrant
-    const uint32_t grp = (warp - 4) >> 2;    // epilogue group 0 .. kGroups-1
-    const int ew = warp - 4;                 // 0..7
+    const int ew = warp - 4;                 // 0 .. kEpiWarps-1
+    const uint32_t grp = (ew >> 2) % kGroups;   // epilogue group
+    const int sel = (ew >> 2) / kGroups;        // which 32-column piece of every 64-column half this warp owns
     const int row = q4 * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
     uint8_t* slab_gen = smem_gen + L.slabs + ew * p.n_slabs * kSlabBytes;
@@ -491,7 +507,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 
     uint32_t lw = 0, Cn = 0, G = 0;
     Tracer tr;
-    tr.init((lane == 0 && q4 == 0) ? p.trace : nullptr, 2 + static_cast<int>(grp));
+    tr.init((lane == 0 && q4 == 0 && sel == 0) ? p.trace : nullptr, 2 + static_cast<int>(grp));
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++lw) {
       const WorkItem it = get_work(p, w);
       tr.ev(1000000ull + w);
@@ -508,7 +524,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           if (is_t0) bulk_wait_read<0>();                 // ... and so did its u_save bulk stores
           epi_bar_sync(1);
         }
-        for (int gq = static_cast<int>(grp); gq < p.R_pad / 16; gq += kGroups) {
+        for (int gq = ew >> 2; gq < p.R_pad / 16; gq += kEpiWarps / 4) {
           uint32_t r[16];
           tmem_ld16(t_lane + gq * 16, r);
           tmem_ld_wait();
@@ -569,9 +585,11 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               }
             } while ((g2 % kGroups) != grp);
           }
-          auto issue_in = [&](int slab, int col, int r0, int strm) {   // lane 0 only
+          auto issue_in = [&](int slab, int col, int r0, int strm) {   // lane 0 only; col = first column of the half
+            int pc = col + sel * kPieceCols;
+            if (pc >= p.Nn) pc = 0;   // this warp's piece lies beyond N (ragged last chunk): load anything, it is ignored
             mbar_arrive_expect_tx(in_bar(ew, slab), kSlabBytes);
-            tma_load_3d(slab_base + slab * kSlabBytes, &tm_in, in_bar(ew, slab), col, r0, need_res && p.res_streams == 1 ? 0 : strm);
+            tma_load_3d(slab_base + slab * kSlabBytes, &tm_in, in_bar(ew, slab), pc, r0, need_res && p.res_streams == 1 ? 0 : strm);
           };
           if (has_in && hc == 0 && lane == 0) issue_in(0, c * p.BN, row0, j);   // very first half of this warp
           tr.ev(5000000ull + ci * 10 + j);   // waiting for accumulator
@@ -590,6 +608,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           const int n_half = (n_eff + 63) >> 6;
           for (int h = 0; h < n_half; ++h) {
             const int col_h = c * p.BN + h * 64;
+            const int col_p = col_h + sel * kPieceCols;   // first column of this warp's piece
             // slabs of this half: y -> ks_y, GELU(y) -> ks_y2. A slab is reused every n_slabs stores; with at most
             // n_slabs - n_out bulk groups still pending the ones that used these slabs have been read.
             constexpr int n_out = dual ? 2 : 1;
@@ -614,10 +633,12 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               }
             }
             __syncwarp();
+            tr.ev(9000000ull + h);   // slabs free / epilogue inputs landed
             uint8_t* sy = slab_gen + ks_y * kSlabBytes;
             uint8_t* sy2 = slab_gen + ks_y2 * kSlabBytes;
-#pragma unroll 2
-            for (int gq = 0; gq < 4; ++gq) {
+#pragma unroll 1
+            for (int g2 = 0; g2 < kPieceGran; ++g2) {
+              const int gq = sel * kPieceGran + g2;   // granule inside the half
               const int n0 = col_h + gq * 16;
               if (n0 >= p.Nn) break;
               const int tcol = h * 64 + gq * 16;
@@ -651,8 +672,8 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 for (int i = 0; i < 16; ++i) v[i] *= rs;
               }
               if (has_in) {
-                const uint4 a0 = *reinterpret_cast<const uint4*>(sy + sw128_offset(lane, gq * 16));
-                const uint4 a1 = *reinterpret_cast<const uint4*>(sy + sw128_offset(lane, gq * 16 + 8));
+                const uint4 a0 = *reinterpret_cast<const uint4*>(sy + sw64_offset(lane, g2 * 16));
+                const uint4 a1 = *reinterpret_cast<const uint4*>(sy + sw64_offset(lane, g2 * 16 + 8));
                 const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
                 if (need_aux) {
                   gelu_grad16_mul(v, aw);
@@ -667,22 +688,24 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               uint32_t pk[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-              *reinterpret_cast<uint4*>(sy + sw128_offset(lane, gq * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              *reinterpret_cast<uint4*>(sy + sw128_offset(lane, gq * 16 + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              *reinterpret_cast<uint4*>(sy + sw64_offset(lane, g2 * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(sy + sw64_offset(lane, g2 * 16 + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
               if (dual) {
                 gelu16_pack(v, pk);
-                *reinterpret_cast<uint4*>(sy2 + sw128_offset(lane, gq * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                *reinterpret_cast<uint4*>(sy2 + sw128_offset(lane, gq * 16 + 8)) =
+                *reinterpret_cast<uint4*>(sy2 + sw64_offset(lane, g2 * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(sy2 + sw64_offset(lane, g2 * 16 + 8)) =
                     make_uint4(pk[4], pk[5], pk[6], pk[7]);
               }
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0 && row0 < p.M) {
-              tma_store_3d(&tm_y, slab_base + ks_y * kSlabBytes, col_h, row0, j);
+            tr.ev(9500000ull + h);   // half computed
+            const bool piece_ok = row0 < p.M && col_p < p.Nn;
+            if (lane == 0) {   // (an empty bulk group keeps the slab-reuse accounting uniform for skipped pieces)
+              if (piece_ok) tma_store_3d(&tm_y, slab_base + ks_y * kSlabBytes, col_p, row0, j);
               bulk_commit();
               if (dual) {
-                tma_store_3d(&tm_y2, slab_base + ks_y2 * kSlabBytes, col_h, row0, j);
+                if (piece_ok) tma_store_3d(&tm_y2, slab_base + ks_y2 * kSlabBytes, col_p, row0, j);
                 bulk_commit();
               }
             }
@@ -698,26 +721,26 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               }
               __syncwarp();
 #pragma unroll 1
-              for (int gq = 0; gq < 4; ++gq) {
-                const int n0 = col_h + gq * 16;
+              for (int g2 = 0; g2 < kPieceGran; ++g2) {
+                const int n0 = col_p + g2 * 16;
                 if (n0 >= p.Nn) break;
                 const uint64_t e0 = static_cast<uint64_t>(grow) * p.Nn + n0;
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
-                  const uint4 mv = *reinterpret_cast<const uint4*>(sy2 + sw128_offset(lane, gq * 16 + hh * 8));
+                  const uint4 mv = *reinterpret_cast<const uint4*>(sy2 + sw64_offset(lane, g2 * 16 + hh * 8));
                   const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
                   uint32_t ow[4];
 #pragma unroll
                   for (int i = 0; i < 4; ++i)
                     ow[i] = dropout_apply_pair(mw[i], p.drop_seed + 1, e0 + hh * 8 + 2 * i, thr, keep_scale);
-                  *reinterpret_cast<uint4*>(sd + sw128_offset(lane, gq * 16 + hh * 8)) =
+                  *reinterpret_cast<uint4*>(sd + sw64_offset(lane, g2 * 16 + hh * 8)) =
                       make_uint4(ow[0], ow[1], ow[2], ow[3]);
                 }
               }
               fence_proxy_async_smem();
               __syncwarp();
-              if (lane == 0 && row0 < p.M) {
-                tma_store_3d(&tm_y2, slab_base + ks_d * kSlabBytes, col_h, row0, p.S_out);
+              if (lane == 0) {
+                if (piece_ok) tma_store_3d(&tm_y2, slab_base + ks_d * kSlabBytes, col_p, row0, p.S_out);
                 bulk_commit();
               }
               slab_k = (slab_k + 1) % p.n_slabs;
@@ -762,9 +785,9 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
-// bf16 row-major [d2][d1][d0] tensor (d0 contiguous), box = (b0, b1, 1), 128-byte swizzle.
+// bf16 row-major [d2][d1][d0] tensor (d0 contiguous), box = (b0, b1, 1), 128-byte swizzle unless stated.
 int make_tmap(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,
-              uint32_t b1) {
+              uint32_t b1, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   auto fn = get_encode_fn();
   MTL_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   MTL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer not 16-byte aligned");
@@ -776,7 +799,7 @@ int make_tmap(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint6
   cuuint32_t box[3] = {b0, b1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MTL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (dims %llu,%llu,%llu box %u,%u)",
               (int)r, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, b0, b1);
@@ -928,10 +951,12 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
     tm_down = tm_w;
     tm_up = tm_w;
   }
-  if (int e = make_tmap(&tm_y, p.y, p.Nn, p.M, p.S_out, 64, 32)) return e;
+  // epilogue slabs: [32 rows x 32 columns] pieces, 64-byte swizzle
+  constexpr CUtensorMapSwizzle kSw64 = CU_TENSOR_MAP_SWIZZLE_64B;
+  if (int e = make_tmap(&tm_y, p.y, p.Nn, p.M, p.S_out, kPieceCols, 32, kSw64)) return e;
   if (p.ep_mode == LIN_EP_GELU_DUAL) {
     MTL_REQUIRE(p.y2 != nullptr, "linear: GELU epilogue needs y2");
-    if (int e = make_tmap(&tm_y2, p.y2, p.Nn, p.M, p.S_out + (p.drop_mode == 1 ? 1 : 0), 64, 32)) return e;
+    if (int e = make_tmap(&tm_y2, p.y2, p.Nn, p.M, p.S_out + (p.drop_mode == 1 ? 1 : 0), kPieceCols, 32, kSw64)) return e;
   } else {
     tm_y2 = tm_y;
   }
@@ -943,9 +968,9 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
   MTL_REQUIRE(!(p.ep_mode == LIN_EP_GELU_BWD && p.res != nullptr), "linear: GELU' epilogue cannot take a residual");
   if (p.ep_mode == LIN_EP_GELU_BWD) {
     MTL_REQUIRE(p.aux != nullptr, "linear: GELU' epilogue needs aux");
-    if (int e = make_tmap(&tm_in, p.aux, p.Nn, p.M, p.S_out, 64, 32)) return e;
+    if (int e = make_tmap(&tm_in, p.aux, p.Nn, p.M, p.S_out, kPieceCols, 32, kSw64)) return e;
   } else if (p.res != nullptr) {
-    if (int e = make_tmap(&tm_in, p.res, p.Nn, p.M, p.res_streams, 64, 32)) return e;
+    if (int e = make_tmap(&tm_in, p.res, p.Nn, p.M, p.res_streams, kPieceCols, 32, kSw64)) return e;
   } else {
     tm_in = tm_y;
   }
