@@ -331,26 +331,57 @@ int mtl_linear_bwd_params(const mtl_linear_cfg* cfg, const void* x, int32_t x_ge
     MTL_REQUIRE(cfg->rows_per_sample > 0 && M % cfg->rows_per_sample == 0,
                 "linear_bwd_params: rows_per_sample=%d does not divide M=%lld", cfg->rows_per_sample, (long long)M);
   const int n_samples = path_scale != nullptr ? static_cast<int>(M / cfg->rows_per_sample) : 0;
-  for (int a = 0; a < L.n; ++a) {
-    const int in = (a == 0 || !xt) ? drop_in : a;
-    // dB_a [N, len] += dy[a]^T (ps[a] * U[:, off:off+len])
-    if (int e = launch_xty(dyb + static_cast<size_t>(a) * M * N, N, ub + L.off[a], L.R_pad, db_cat + L.off[a], L.R_pad, M,
-                           N, L.len[a], path_scale ? path_scale + static_cast<size_t>(a) * n_samples : nullptr,
-                           cfg->rows_per_sample, 0, 1.f, S(stream)))
-      return e;
-    // dA_a [len, K] += G[:, off:off+len]^T (ps[a] * x_in(a))     (G carries the adapter scale, not the path scale)
-    if (int e = launch_xty(gb + L.off[a], L.R_pad, xb + static_cast<size_t>(in) * M * K, K,
-                           da_cat + static_cast<size_t>(L.off[a]) * K, K, M, L.len[a], K,
-                           path_scale ? path_scale + static_cast<size_t>(a) * n_samples : nullptr, cfg->rows_per_sample,
-                           x_gelu, 1.f, S(stream)))
-      return e;
+  if (x_gelu || K < 72 || N < 72) {
+    // legacy path (mma.sync): GELU recomputation on load, or operands too narrow for the 128-column UMMA tile
+    for (int a = 0; a < L.n; ++a) {
+      const int in = (a == 0 || !xt) ? drop_in : a;
+      // dB_a [N, len] += dy[a]^T (ps[a] * U[:, off:off+len])
+      if (int e = launch_xty(dyb + static_cast<size_t>(a) * M * N, N, ub + L.off[a], L.R_pad, db_cat + L.off[a], L.R_pad,
+                             M, N, L.len[a], path_scale ? path_scale + static_cast<size_t>(a) * n_samples : nullptr,
+                             cfg->rows_per_sample, 0, 1.f, S(stream)))
+        return e;
+      // dA_a [len, K] += G[:, off:off+len]^T (ps[a] * x_in(a))     (G carries the adapter scale, not the path scale)
+      if (int e = launch_xty(gb + L.off[a], L.R_pad, xb + static_cast<size_t>(in) * M * K, K,
+                             da_cat + static_cast<size_t>(L.off[a]) * K, K, M, L.len[a], K,
+                             path_scale ? path_scale + static_cast<size_t>(a) * n_samples : nullptr,
+                             cfg->rows_per_sample, x_gelu, 1.f, S(stream)))
+        return e;
+    }
+    return 0;
   }
-  return 0;
+  // one tcgen05 launch for every adapter: wide operands dy (dB) and x (dA), rank operands U and G
+  XtyOperand wide[2] = {{dyb, N, 0, out_streams(cfg)}, {xb, K, 0, S_in}};
+  XtyOperand rank[2] = {{ub, L.R_pad, 0, 1}, {gb, L.R_pad, 0, 1}};
+  XtyJobGroup grp[2 * (1 + MTL_MAX_TASKS)];
+  int ng = 0;
+  for (int a = 0; a < L.n; ++a)   // dB_a [N, len] += dy[a]^T (ps[a] * U[:, off:off+len])
+    grp[ng++] = XtyJobGroup{0, a, 0, L.off[a], L.len[a], 0, L.R_pad, db_cat,
+                            path_scale ? path_scale + static_cast<size_t>(a) * n_samples : nullptr};
+  if (!xt && (path_scale == nullptr || L.n == 1)) {
+    // every adapter consumed the same input stream: dA_cat [R, K] += G^T (ps * x) in one group
+    grp[ng++] = XtyJobGroup{1, drop_in, 1, 0, L.R_pad, 1, K, da_cat, path_scale};
+  } else {
+    for (int a = 0; a < L.n; ++a) {   // dA_a [len, K] += (ps[a] * G[:, off:off+len])^T x_in(a)
+      const int in = (a == 0 || !xt) ? drop_in : a;
+      grp[ng++] = XtyJobGroup{1, in, 1, L.off[a], L.len[a], 1, K, da_cat,
+                              path_scale ? path_scale + static_cast<size_t>(a) * n_samples : nullptr};
+    }
+  }
+  return launch_xty_groups(wide, rank, grp, ng, M, cfg->rows_per_sample, S(stream));
 }
 
 int mtl_xty(const void* p, int64_t ldp, const void* q, int64_t ldq, float* c, int64_t ldc, int64_t M, int32_t a,
             int32_t b, float alpha, mtl_stream_t stream) {
   MTL_REQUIRE(p != nullptr && q != nullptr && c != nullptr, "xty: NULL argument");
+  const bool q_wide = b >= a;
+  const int wide_cols = q_wide ? b : a, rank_cols = q_wide ? a : b;
+  if (alpha == 1.f && wide_cols >= 72 && rank_cols % 4 == 0 && ldp % 8 == 0 && ldq % 8 == 0 && M < (1ll << 31)) {
+    // C[a, b]: wide = the larger dimension (128-column UMMA tiles), rank = the other (64-column chunks)
+    XtyOperand wide[2] = {{q_wide ? q : p, wide_cols, q_wide ? ldq : ldp, 1}, {nullptr, 0, 0, 0}};
+    XtyOperand rank[2] = {{q_wide ? p : q, rank_cols, q_wide ? ldp : ldq, 1}, {nullptr, 0, 0, 0}};
+    XtyJobGroup g{0, 0, 0, 0, rank_cols, q_wide ? 1 : 0, static_cast<int>(ldc), c, nullptr};
+    return launch_xty_groups(wide, rank, &g, 1, M, 0, S(stream));
+  }
   return launch_xty(p, ldp, q, ldq, c, ldc, M, a, b, nullptr, 0, 0, alpha, S(stream));
 }
 

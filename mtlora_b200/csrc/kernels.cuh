@@ -51,4 +51,23 @@ int launch_cast_transpose(const float* w, void* w_bf16, void* wt_bf16, int rows,
 int launch_xty(const void* P, long ldp, const void* Q, long ldq, float* C, long ldc, long M, int a, int b,
                const float* rowscale, int rows_per_sample, int q_gelu, float alpha, cudaStream_t stream);
 
+// xty_sm100.cu ------------------------------------------------------------------------------------
+// out[w, r] += sum_m Wide[m, w] * (rowscale(m) * Rank[m, r]) for a list of job groups in ONE launch (tcgen05, both
+// operands consumed MN-major straight from their row-major layout). Operands are bf16 [streams][M][pitch].
+struct XtyOperand {
+  const void* base;   // null: unused slot
+  int cols;           // valid columns
+  long pitch;         // elements between rows (0: cols)
+  int streams;        // wide operands: >= 1 (3rd TMA coordinate); rank operands: ignored
+};
+struct XtyJobGroup {
+  int wide_op, wide_stream;    // which wide operand (0/1) and stream
+  int rank_op, r0, rlen;       // which rank operand (0/1), its column range [r0, r0 + rlen)
+  int out_rank_major, out_ld;  // 0: out[w * ld + r], 1: out[r * ld + w]   (r = absolute rank column)
+  float* out;
+  const float* rowscale;       // per-sample scale of the contraction rows (DropPath), or null
+};
+int launch_xty_groups(const XtyOperand* wide, const XtyOperand* rank, const XtyJobGroup* groups, int n_groups,
+                      long M, int rows_per_sample, cudaStream_t stream);
+
 }  // namespace mtl

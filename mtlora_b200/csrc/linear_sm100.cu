@@ -769,9 +769,12 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   }
 }
 
+}  // namespace
+
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
+namespace {
 PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   static std::once_flag once;
@@ -785,17 +788,21 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
+}  // namespace
+
 // bf16 row-major [d2][d1][d0] tensor (d0 contiguous), box = (b0, b1, 1), 128-byte swizzle unless stated.
+// pitch = elements between consecutive rows (0: d0, i.e. densely packed).
 int make_tmap(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,
-              uint32_t b1, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+              uint32_t b1, CUtensorMapSwizzle swz, uint64_t pitch) {
+  if (pitch == 0) pitch = d0;
   auto fn = get_encode_fn();
   MTL_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   MTL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer not 16-byte aligned");
-  MTL_REQUIRE((d0 * 2) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes (inner dim %llu)",
-              (unsigned long long)d0);
+  MTL_REQUIRE((pitch * 2) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes (pitch %llu elements)",
+              (unsigned long long)pitch);
   const int rank = d2 > 0 ? 3 : 2;
   cuuint64_t dims[3] = {d0, d1, d2 > 0 ? d2 : 1};
-  cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+  cuuint64_t strides[2] = {pitch * 2, pitch * d1 * 2};
   cuuint32_t box[3] = {b0, b1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box,
@@ -806,8 +813,8 @@ int make_tmap(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint6
   return 0;
 }
 
+namespace {
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
-
 }  // namespace
 
 int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, const void* up,

@@ -81,6 +81,11 @@ struct LinPlan {
   int force_split;  // keep dense and adapter accumulators in separate TMEM regions even if S_out == 1
 };
 
+// TMA descriptor of a bf16 row-major [d2][d1][d0] tensor (d0 contiguous, `pitch` elements between rows, 0 = dense),
+// box = (b0, b1, 1). Shared by the linear and the adapter-gradient kernels.
+int make_tmap(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+              CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, uint64_t pitch = 0);
+
 // Host side: fills the derived tiling fields of `plan`, encodes tensor maps, launches.
 // x: [S_in, M, Kc], wm: [Nn, Kc], down: [R_pad, Kc], up: [Nn, R_pad]; all bf16 row-major.
 int launch_linear(LinPlan plan, const void* x, const void* wm, const void* down, const void* up,
