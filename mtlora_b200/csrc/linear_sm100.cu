@@ -102,6 +102,11 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -642,11 +647,23 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               const int n0 = col_h + gq * 16;
               if (n0 >= p.Nn) break;
               const int tcol = h * 64 + gq * 16;
+              // every load of the granule is issued before the TMEM wait so that the latencies overlap
               uint32_t pr[16], dr[16];
               if (use_p) tmem_ld16(acc_p + tcol, pr);
               tmem_ld16(acc_d + tcol, dr);
+              float4 bv[4];
+              if (p.bias != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
+              }
+              uint32_t aw[8];
+              if (has_in) {
+                const uint4 a0 = *reinterpret_cast<const uint4*>(sy + sw64_offset(lane, g2 * 16));
+                const uint4 a1 = *reinterpret_cast<const uint4*>(sy + sw64_offset(lane, g2 * 16 + 8));
+                aw[0] = a0.x; aw[1] = a0.y; aw[2] = a0.z; aw[3] = a0.w;
+                aw[4] = a1.x; aw[5] = a1.y; aw[6] = a1.z; aw[7] = a1.w;
+              }
               tmem_ld_wait();
-              float v[16];
               if (mask_delta) {
                 const uint64_t e0 = (static_cast<uint64_t>(grow) * p.Nn + n0) >> 1;
 #pragma unroll
@@ -657,34 +674,33 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                       (hsh & 0xffff0000u) >= thr ? __float_as_uint(__uint_as_float(dr[2 * i + 1]) * keep_scale) : 0u;
                 }
               }
+              // packed fp32x2 arithmetic: two columns per instruction
+              uint64_t v2[8];
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                v[i] = use_p ? __uint_as_float(dr[i]) + __uint_as_float(pr[i]) : __uint_as_float(dr[i]);
+              for (int i = 0; i < 8; ++i) {
+                v2[i] = pack2(__uint_as_float(dr[2 * i]), __uint_as_float(dr[2 * i + 1]));
+                if (use_p) v2[i] = add2(v2[i], pack2(__uint_as_float(pr[2 * i]), __uint_as_float(pr[2 * i + 1])));
+              }
               if (p.bias != nullptr) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
-                  v[4 * i + 0] += bv.x; v[4 * i + 1] += bv.y; v[4 * i + 2] += bv.z; v[4 * i + 3] += bv.w;
+                  v2[2 * i] = add2(v2[2 * i], pack2(bv[i].x, bv[i].y));
+                  v2[2 * i + 1] = add2(v2[2 * i + 1], pack2(bv[i].z, bv[i].w));
                 }
               }
               if (p.rowscale_out != nullptr) {
+                const uint64_t rs2 = pack2(rs, rs);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] *= rs;
+                for (int i = 0; i < 8; ++i) v2[i] = mul2(v2[i], rs2);
               }
-              if (has_in) {
-                const uint4 a0 = *reinterpret_cast<const uint4*>(sy + sw64_offset(lane, g2 * 16));
-                const uint4 a1 = *reinterpret_cast<const uint4*>(sy + sw64_offset(lane, g2 * 16 + 8));
-                const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                if (need_aux) {
-                  gelu_grad16_mul(v, aw);
-                } else {
+              if (has_in && !need_aux) {
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    v[2 * i] += bf16lo_to_f32(aw[i]);
-                    v[2 * i + 1] += bf16hi_to_f32(aw[i]);
-                  }
-                }
+                for (int i = 0; i < 8; ++i) v2[i] = add2(v2[i], pack2(bf16lo_to_f32(aw[i]), bf16hi_to_f32(aw[i])));
               }
+              float v[16];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) unpack2(v2[i], v[2 * i], v[2 * i + 1]);
+              if (need_aux) gelu_grad16_mul(v, aw);
               uint32_t pk[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);

@@ -806,8 +806,35 @@ class BasicLayer(nn.Module):
 # ----------------------------------------------------------------------------------------------------------------
 # PatchEmbed — reference :568-621 (stays PyTorch: Conv2d + LayerNorm, not on the replaced path)
 # ----------------------------------------------------------------------------------------------------------------
+class _LayerNormFn(torch.autograd.Function):
+    """Stand-alone LayerNorm over the last dim through mtl_layernorm_fwd / _bwd (bf16 rows, fp32 statistics)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        C = x.shape[-1]
+        x2 = x.reshape(-1, C)
+        w, b = weight.detach().float(), bias.detach().float()
+        y, mean, rstd = ops.layernorm_fwd(x2, w, b, eps)
+        ctx.save_for_backward(x2, w, mean, rstd)
+        ctx.want = weight.requires_grad or bias.requires_grad
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, mean, rstd = ctx.saved_tensors
+        dy2 = dy.reshape(x2.shape)
+        if dy2.dtype != BF16 or not dy2.is_contiguous():
+            dy2 = dy2.to(BF16).contiguous()
+        dx, dw, db = ops.layernorm_bwd(dy2, x2, w, mean, rstd, want_param_grads=ctx.want)
+        return dx.view(dy.shape), dw, db, None
+
+
 class PatchEmbed(nn.Module):
-    r"""Image to Patch Embedding"""
+    r"""Image to Patch Embedding (reference :568-611: Conv2d k4 s4 + LayerNorm; the convolution stays PyTorch / cuDNN).
+
+    Under bf16 autocast on CUDA the convolution runs channels-last, so its output already is the (B, L, C) token
+    matrix, and the LayerNorm goes through mtl_layernorm_fwd / _bwd in bf16 (one HBM pass) instead of autocast's fp32
+    LayerNorm over a strided view."""
 
     def __init__(self, img_size=224, patch_size=4, in_chans=3, embed_dim=96, norm_layer=None):
         super().__init__()
@@ -827,6 +854,12 @@ class PatchEmbed(nn.Module):
         B, C, H, W = x.shape
         assert H == self.img_size[0] and W == self.img_size[1], \
             f"Input image size ({H}*{W}) doesn't match model ({self.img_size[0]}*{self.img_size[1]})."
+        if (x.is_cuda and type(self.norm) is nn.LayerNorm and torch.is_autocast_enabled()
+                and torch.get_autocast_gpu_dtype() == BF16):
+            y = self.proj(x.contiguous(memory_format=torch.channels_last))   # (B, C, Ph, Pw) bf16, NHWC strides
+            y = y.permute(0, 2, 3, 1).contiguous()                           # no copy when the conv answered NHWC
+            y = y.view(B, -1, self.embed_dim)
+            return _LayerNormFn.apply(y, self.norm.weight, self.norm.bias, self.norm.eps)
         x = self.proj(x).flatten(2).transpose(1, 2)  # B Ph*Pw C
         if self.norm is not None:
             x = self.norm(x)
