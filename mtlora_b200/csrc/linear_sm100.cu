@@ -78,6 +78,14 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int
                "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_l2_3d(const void* tmap, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void group_bar_sync(int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(32 * kGroupWarps) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
@@ -184,23 +192,34 @@ struct WorkItem {
   int m0, split, n_my_chunks;
 };
 // Debug timeline (MTL_LINEAR_TRACE=<file>): CTA 0 records (globaltimer, code) pairs per role.
+template <bool ON>
 struct Tracer {
   unsigned long long* buf;
   int n;
   __device__ __forceinline__ void init(unsigned long long* base, int role) {
-    buf = (base != nullptr && blockIdx.x == 0) ? base + role * 2048 : nullptr;
-    n = 0;
+    if constexpr (ON) {
+      buf = (base != nullptr && blockIdx.x == 0) ? base + role * 2048 : nullptr;
+      n = 0;
+    }
   }
   __device__ __forceinline__ void ev(unsigned long long code) {
-    if (buf != nullptr && n < 1023) {
-      buf[2 * n] = globaltimer_ns();
-      buf[2 * n + 1] = code;
-      ++n;
+    if constexpr (ON) {
+      if (buf != nullptr && n < 1023) {
+        buf[2 * n] = globaltimer_ns();
+        buf[2 * n + 1] = code;
+        ++n;
+      }
     }
   }
 };
 __device__ __forceinline__ WorkItem get_work(const LinPlan& p, int w) {
   WorkItem it;
+  if (p.n_splits == 1) {   // the common case (many row tiles): no integer divisions on the per-item path
+    it.split = 0;
+    it.m0 = w * LIN_BM;
+    it.n_my_chunks = p.n_chunks;
+    return it;
+  }
   const int m_tile = w / p.n_splits;
   it.split = w - m_tile * p.n_splits;
   it.m0 = m_tile * LIN_BM;
@@ -210,13 +229,13 @@ __device__ __forceinline__ WorkItem get_work(const LinPlan& p, int w) {
 
 // EP: LinEpilogue; HAS_RES: a residual tensor is added in the epilogue (compile-time specialisation keeps the
 // per-element instruction count of the epilogue — the bottleneck of the wide stage-0/1 layers — minimal)
-template <int EP, bool HAS_RES>
+template <int EP, bool HAS_RES, bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1)
 mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                   const __grid_constant__ CUtensorMap tm_down, const __grid_constant__ CUtensorMap tm_up,
                   const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_y2,
                   const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_in,
-                  const __grid_constant__ LinPlan p) {
+                  const __grid_constant__ CUtensorMap tm_pf, const __grid_constant__ LinPlan p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -299,11 +318,18 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           phase ^= 1u;
         }
       };
-      Tracer tr;
+      Tracer<TRACE> tr;
       tr.init(p.trace, 0);
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         const WorkItem it = get_work(p, w);
         tr.ev(1000000ull + w);
+        // epilogue inputs of this work item (residual / GELU' argument): pull them into L2 now, their consumers run
+        // several microseconds from now
+        for (int sj = 0; sj < p.in_streams; ++sj)
+          for (int ci = 0; ci < it.n_my_chunks; ++ci) {
+            const int c0 = (it.split + ci * p.n_splits) * p.BN;
+            for (int hcol = c0; hcol < c0 + p.BN && hcol < p.Nn; hcol += 64) tma_prefetch_l2_3d(&tm_pf, hcol, it.m0, sj);
+          }
         // phase 1: rank-space ("down") products
         for (int g = 0; g < p.n_groups; ++g) {
           const int len = p.grp_len[g];
@@ -356,7 +382,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         }
       };
       uint32_t lw = 0, Cn = 0, G = 0;  // local work / chunk / item counters (same sequence in the epilogue warps)
-      Tracer tr;
+      Tracer<TRACE> tr;
       tr.init(p.trace, 1);
       for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++lw) {
         const WorkItem it = get_work(p, w);
@@ -503,7 +529,11 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     uint8_t* slab_gen = smem_gen + L.slabs + ew * p.n_slabs * kSlabBytes;
     const uint32_t slab_base = smem_base + L.slabs + ew * p.n_slabs * kSlabBytes;
     int slab_k = 0;
-    uint32_t hc = 0;   // halves processed by this warp (slab rotation / input-barrier phase when has_in)
+    bool first_half = true;
+    uint32_t in_ph = 0;   // phase bit of every epilogue-input slab barrier of this warp
+    auto nxt_slab = [&](int k) { return k + 1 == p.n_slabs ? 0 : k + 1; };
+    const bool grp_leader = (sel == 0 && q4 == 0);   // the one warp of the group that polls the accumulator barriers
+    const uint32_t dsh = p.n_dbuf - 1, psh = p.n_pbuf > 0 ? p.n_pbuf - 1 : 0;   // n_dbuf, n_pbuf in {1, 2}
     const bool is_t0 = (warp == 4 && lane == 0);
     const uint32_t thr = dropout_threshold(p.drop_p);
     const float keep_scale = 1.f / (1.f - p.drop_p);
@@ -511,7 +541,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     constexpr bool dual = EP == LIN_EP_GELU_DUAL;
 
     uint32_t lw = 0, Cn = 0, G = 0;
-    Tracer tr;
+    Tracer<TRACE> tr;
     tr.init((lane == 0 && q4 == 0 && sel == 0) ? p.trace : nullptr, 2 + static_cast<int>(grp));
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++lw) {
       const WorkItem it = get_work(p, w);
@@ -522,13 +552,13 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const int row0 = it.m0 + q4 * 32;
 
       if (p.R_pad > 0) {
-        mbar_wait(u_full, lw & 1u, p.wait_hint_ns);
-        tc_fence_after();
-        if (lw > 0) mbar_wait(usm_free, (lw - 1) & 1u, p.wait_hint_ns);  // previous item's delta MMAs finished reading usm
-        if (p.u_save != nullptr) {
-          if (is_t0) bulk_wait_read<0>();                 // ... and so did its u_save bulk stores
-          epi_bar_sync(1);
+        if (warp == 4) {   // one warp polls, the other epilogue warps block on the named barrier (no issue slots)
+          mbar_wait(u_full, lw & 1u, p.wait_hint_ns);
+          if (lw > 0) mbar_wait(usm_free, (lw - 1) & 1u, p.wait_hint_ns);  // previous item's delta MMAs finished reading usm
+          if (p.u_save != nullptr && lane == 0) bulk_wait_read<0>();       // ... and so did its u_save bulk stores
         }
+        epi_bar_sync(1);
+        tc_fence_after();
         for (int gq = ew >> 2; gq < p.R_pad / 16; gq += kEpiWarps / 4) {
           uint32_t r[16];
           tmem_ld16(t_lane + gq * 16, r);
@@ -562,11 +592,11 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         int n_eff = p.Nn - c * p.BN;
         if (n_eff > p.BN) n_eff = p.BN;
         const int n_items = multi ? p.S_out : 1;
-        const uint32_t pb = multi ? (Cn % p.n_pbuf) : 0;
+        const uint32_t pb = multi ? (Cn & psh) : 0;
         bool p_waited = false;
         for (int j = 0; j < n_items; ++j, ++G) {
           if ((G % kGroups) != grp) continue;
-          const uint32_t kk = G / kGroups, dbuf = kk % p.n_dbuf, db = grp * 2 + dbuf;
+          const uint32_t kk = G / kGroups, dbuf = kk & dsh, db = grp * 2 + dbuf;
           // Epilogue inputs that do not depend on the accumulators (the GELU' argument of the fc2 backward, the residual
           // of proj / fc2 forward) are staged by TMA into the very slab the half's output will be written to, one
           // 64-column half ahead (across item and tile boundaries), so their HBM latency never stalls the math.
@@ -596,15 +626,16 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             mbar_arrive_expect_tx(in_bar(ew, slab), kSlabBytes);
             tma_load_3d(slab_base + slab * kSlabBytes, &tm_in, in_bar(ew, slab), pc, r0, need_res && p.res_streams == 1 ? 0 : strm);
           };
-          if (has_in && hc == 0 && lane == 0) issue_in(0, c * p.BN, row0, j);   // very first half of this warp
+          if (has_in && first_half && lane == 0) issue_in(0, c * p.BN, row0, j);   // very first half of this warp
           tr.ev(5000000ull + ci * 10 + j);   // waiting for accumulator
-          mbar_wait(d_full(db), (kk / p.n_dbuf) & 1u, p.wait_hint_ns);
-          tr.ev(6000000ull + ci * 10 + j);   // got it
           const bool use_p = multi && p.out_useP[j];
-          if (use_p && !p_waited) {
-            mbar_wait(p_full(pb), (Cn / p.n_pbuf) & 1u, p.wait_hint_ns);
-            p_waited = true;
+          if (grp_leader) {
+            mbar_wait(d_full(db), (kk >> dsh) & 1u, p.wait_hint_ns);
+            if (use_p && !p_waited) mbar_wait(p_full(pb), (Cn >> psh) & 1u, p.wait_hint_ns);
           }
+          if (use_p) p_waited = true;
+          group_bar_sync(3 + static_cast<int>(grp));
+          tr.ev(6000000ull + ci * 10 + j);   // got it
           tc_fence_after();
           const uint32_t acc_d = t_lane + d_col0 + (grp * p.n_dbuf + dbuf) * p.BN;
           const uint32_t acc_p = t_lane + p_col0 + pb * p.BN;
@@ -618,10 +649,10 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             // n_slabs - n_out bulk groups still pending the ones that used these slabs have been read.
             constexpr int n_out = dual ? 2 : 1;
             const int ks_y = slab_k;
-            const int ks_y2 = (slab_k + 1) % p.n_slabs;
+            const int ks_y2 = nxt_slab(slab_k);
             if (has_in) {
               // next half of this warp: same item, or the first half of the group's next item
-              const int ks_n = (slab_k + 1) % p.n_slabs;
+              const int ks_n = ks_y2;
               if (lane == 0) {
                 if (p.n_slabs >= 3) bulk_wait_read<1>(); else bulk_wait_read<0>();   // slab ks_n's last store was read
                 if (h + 1 < n_half) {
@@ -631,7 +662,8 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                   issue_in(ks_n, (ni.split + nx_ci * p.n_splits) * p.BN, ni.m0 + q4 * 32, nx_j);
                 }
               }
-              mbar_wait(in_bar(ew, ks_y), (hc / p.n_slabs) & 1u, p.wait_hint_ns);
+              mbar_wait(in_bar(ew, ks_y), (in_ph >> ks_y) & 1u, p.wait_hint_ns);
+              in_ph ^= 1u << ks_y;
             } else {
               if (lane == 0) {
                 if (p.n_slabs - n_out >= 1) bulk_wait_read<1>(); else bulk_wait_read<0>();
@@ -725,8 +757,8 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 bulk_commit();
               }
             }
-            slab_k = (slab_k + n_out) % p.n_slabs;
-            ++hc;
+            slab_k = dual ? nxt_slab(ks_y2) : ks_y2;
+            first_half = false;
             if (dual && p.drop_mode == 1 && j == 0) {
               // D(m) of the shared stream (LoRA dropout of the consuming fc2, drawn with seed + 1): derived from the
               // bf16-rounded activation in the y2 slab so that it equals dropout(y2, seed + 1) exactly
@@ -759,7 +791,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 if (piece_ok) tma_store_3d(&tm_y2, slab_base + ks_d * kSlabBytes, col_p, row0, p.S_out);
                 bulk_commit();
               }
-              slab_k = (slab_k + 1) % p.n_slabs;
+              slab_k = nxt_slab(slab_k);
             }
           }
           tc_fence_before();
@@ -964,7 +996,7 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
   MTL_REQUIRE(smem_bytes <= 227 * 1024, "linear: shared memory %u exceeds 227 KiB", smem_bytes);
 
   // ---- tensor maps ---------------------------------------------------------------------------
-  CUtensorMap tm_x, tm_w, tm_down, tm_up, tm_y, tm_y2, tm_u, tm_in;
+  CUtensorMap tm_x, tm_w, tm_down, tm_up, tm_y, tm_y2, tm_u, tm_in, tm_pf;
   if (int e = make_tmap(&tm_x, x, p.Kc, p.M, p.S_in, LIN_BK, LIN_BM)) return e;
   if (int e = make_tmap(&tm_w, wm, p.Kc, p.Nn, 0, LIN_BK, p.BN)) return e;
   if (p.R_pad > 0) {
@@ -989,31 +1021,43 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
     tm_u = tm_y;
   }
   MTL_REQUIRE(!(p.ep_mode == LIN_EP_GELU_BWD && p.res != nullptr), "linear: GELU' epilogue cannot take a residual");
+  // tm_pf: the same tensor with [128 rows x 64 columns] boxes, used by the producer to prefetch the epilogue inputs
+  // of a work item into L2 while its accumulators are still being formed
   if (p.ep_mode == LIN_EP_GELU_BWD) {
     MTL_REQUIRE(p.aux != nullptr, "linear: GELU' epilogue needs aux");
     if (int e = make_tmap(&tm_in, p.aux, p.Nn, p.M, p.S_out, kPieceCols, 32, kSw64)) return e;
+    if (int e = make_tmap(&tm_pf, p.aux, p.Nn, p.M, p.S_out, 64, LIN_BM, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+    p.in_streams = p.S_out;
   } else if (p.res != nullptr) {
     if (int e = make_tmap(&tm_in, p.res, p.Nn, p.M, p.res_streams, kPieceCols, 32, kSw64)) return e;
+    if (int e = make_tmap(&tm_pf, p.res, p.Nn, p.M, p.res_streams, 64, LIN_BM, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+    p.in_streams = p.res_streams;
   } else {
     tm_in = tm_y;
+    tm_pf = tm_y;
+    p.in_streams = 0;
   }
 
   using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
-                            CUtensorMap, LinPlan);
-  static KernelFn kernels[3][2] = {
-      {mtl_linear_kernel<LIN_EP_NONE, false>, mtl_linear_kernel<LIN_EP_NONE, true>},
-      {mtl_linear_kernel<LIN_EP_GELU_DUAL, false>, mtl_linear_kernel<LIN_EP_GELU_DUAL, true>},
-      {mtl_linear_kernel<LIN_EP_GELU_BWD, false>, mtl_linear_kernel<LIN_EP_GELU_BWD, true>}};
+                            CUtensorMap, CUtensorMap, LinPlan);
+  static KernelFn kernels[3][2][2] = {
+      {{mtl_linear_kernel<LIN_EP_NONE, false, false>, mtl_linear_kernel<LIN_EP_NONE, false, true>},
+       {mtl_linear_kernel<LIN_EP_NONE, true, false>, mtl_linear_kernel<LIN_EP_NONE, true, true>}},
+      {{mtl_linear_kernel<LIN_EP_GELU_DUAL, false, false>, mtl_linear_kernel<LIN_EP_GELU_DUAL, false, true>},
+       {mtl_linear_kernel<LIN_EP_GELU_DUAL, true, false>, mtl_linear_kernel<LIN_EP_GELU_DUAL, true, true>}},
+      {{mtl_linear_kernel<LIN_EP_GELU_BWD, false, false>, mtl_linear_kernel<LIN_EP_GELU_BWD, false, true>},
+       {mtl_linear_kernel<LIN_EP_GELU_BWD, true, false>, mtl_linear_kernel<LIN_EP_GELU_BWD, true, true>}}};
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   static int max_ctas = -1;
   static uint32_t wait_hint = 1000u;
   std::call_once(attr_once, []() {
     for (int a = 0; a < 3; ++a)
-      for (int b = 0; b < 2; ++b) {
-        cudaError_t e = cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) attr_err = e;
-      }
+      for (int b = 0; b < 2; ++b)
+        for (int c = 0; c < 2; ++c) {
+          cudaError_t e = cudaFuncSetAttribute(kernels[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+          if (e != cudaSuccess) attr_err = e;
+        }
     const char* e = getenv("MTL_LINEAR_MAX_CTAS");  // debugging aid: 0 = one CTA per work item (non-persistent)
     max_ctas = e ? atoi(e) : -1;
     const char* h = getenv("MTL_WAIT_HINT_NS");      // mbarrier.try_wait suspend-time hint (tuning aid)
@@ -1032,8 +1076,8 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
   int grid = p.n_work < n_sm ? p.n_work : n_sm;
   if (max_ctas == 0) grid = p.n_work;
   else if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  kernels[p.ep_mode][p.res != nullptr ? 1 : 0]<<<grid, kThreads, smem_bytes, stream>>>(tm_x, tm_w, tm_down, tm_up, tm_y,
-                                                                                      tm_y2, tm_u, tm_in, p);
+  kernels[p.ep_mode][p.res != nullptr ? 1 : 0][p.trace != nullptr ? 1 : 0]<<<grid, kThreads, smem_bytes, stream>>>(
+      tm_x, tm_w, tm_down, tm_up, tm_y, tm_y2, tm_u, tm_in, tm_pf, p);
   note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
   if (p.trace != nullptr) {   // debugging only: synchronous dump of CTA 0's timeline (last launch wins)

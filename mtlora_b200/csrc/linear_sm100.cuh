@@ -65,6 +65,7 @@ struct LinPlan {
   const __nv_bfloat16* aux;   // [S_out, M, Nn] (GELU_BWD)
   const __nv_bfloat16* res;   // [res_streams, M, Nn] residual added last, or null
   int res_streams;            // 1 (shared by all outputs) or S_out
+  int in_streams;             // streams of the epilogue-input tensor (aux / res) the producer prefetches into L2
   const float* rowscale_out;  // [S_out, n_samples] multiplies the accumulator (DropPath), or null
   const float* rowscale_in;   // [S_in, n_samples] multiplies U rows, or null
   int rows_per_sample, n_samples;
