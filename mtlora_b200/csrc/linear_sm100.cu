@@ -474,10 +474,17 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               uint32_t db = 0;
               if (multi) {
                 const uint32_t k = G / kGroups;
-                db = (G % kGroups) * 2 + k % p.n_dbuf;
-                mbar_wait(d_empty(db), ((k / p.n_dbuf) & 1u) ^ 1u, p.wait_hint_ns);
-                tc_fence_after();
-                acc = tmem_base + d_col0 + ((G % kGroups) * p.n_dbuf + k % p.n_dbuf) * p.BN;
+                if (p.d_shared) {   // one delta accumulator serves both groups (item G is its G-th use)
+                  db = 0;
+                  mbar_wait(d_empty(0), (G & 1u) ^ 1u, p.wait_hint_ns);
+                  tc_fence_after();
+                  acc = tmem_base + d_col0;
+                } else {
+                  db = (G % kGroups) * 2 + k % p.n_dbuf;
+                  mbar_wait(d_empty(db), ((k / p.n_dbuf) & 1u) ^ 1u, p.wait_hint_ns);
+                  tc_fence_after();
+                  acc = tmem_base + d_col0 + ((G % kGroups) * p.n_dbuf + k % p.n_dbuf) * p.BN;
+                }
                 started = false;
               } else {
                 acc = acc_dense;
@@ -596,7 +603,8 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         bool p_waited = false;
         for (int j = 0; j < n_items; ++j, ++G) {
           if ((G % kGroups) != grp) continue;
-          const uint32_t kk = G / kGroups, dbuf = kk & dsh, db = grp * 2 + dbuf;
+          const uint32_t kk = G / kGroups, dbuf = kk & dsh, db = p.d_shared ? 0u : grp * 2 + dbuf;
+          const uint32_t d_parity = p.d_shared ? (G & 1u) : ((kk >> dsh) & 1u);
           // Epilogue inputs that do not depend on the accumulators (the GELU' argument of the fc2 backward, the residual
           // of proj / fc2 forward) are staged by TMA into the very slab the half's output will be written to, one
           // 64-column half ahead (across item and tile boundaries), so their HBM latency never stalls the math.
@@ -630,14 +638,14 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           tr.ev(5000000ull + ci * 10 + j);   // waiting for accumulator
           const bool use_p = multi && p.out_useP[j];
           if (grp_leader) {
-            mbar_wait(d_full(db), (kk >> dsh) & 1u, p.wait_hint_ns);
+            mbar_wait(d_full(db), d_parity, p.wait_hint_ns);
             if (use_p && !p_waited) mbar_wait(p_full(pb), (Cn >> psh) & 1u, p.wait_hint_ns);
           }
           if (use_p) p_waited = true;
           group_bar_sync(3 + static_cast<int>(grp));
           tr.ev(6000000ull + ci * 10 + j);   // got it
           tc_fence_after();
-          const uint32_t acc_d = t_lane + d_col0 + (grp * p.n_dbuf + dbuf) * p.BN;
+          const uint32_t acc_d = t_lane + d_col0 + (p.d_shared ? 0u : (grp * p.n_dbuf + dbuf) * p.BN);
           const uint32_t acc_p = t_lane + p_col0 + pb * p.BN;
           const bool mask_delta = multi && (p.drop_mode == 2) && j == 0;
           const float rs = (p.rowscale_out != nullptr) ? p.rowscale_out[j * p.n_samples + sample] : 1.f;
@@ -915,6 +923,17 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
     }
     if (cols(bn, p.n_pbuf, 1) > 512) p.n_pbuf = 1;
     if (cols(bn, p.n_pbuf, 2) <= 512) p.n_dbuf = 2;
+    // single output stream with separate dense / adapter accumulators (input gradient with LoRA dropout) and a long
+    // contraction: 128-column chunks halve the re-streaming of the X tile from L2. The dense accumulator stays
+    // double-buffered; ONE delta accumulator serves both epilogue groups (its MMAs are tiny, so waiting for the
+    // previous item's epilogue before issuing them costs next to nothing).
+    if (heavy && p.S_out == 1 && p.Nn > 64 && u_cols + 3 * 128 <= 512 && fits_smem(128, want_slabs) &&
+        getenv("MTL_LINEAR_NO_DSHARED") == nullptr) {
+      bn = 128;
+      p.n_pbuf = 2;
+      p.n_dbuf = 1;
+      p.d_shared = 1;
+    }
   }
   if (const char* e = getenv("MTL_LINEAR_BN")) {   // tuning aid: force the chunk width (merged mode only)
     const int fb = atoi(e);
@@ -926,7 +945,7 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
   p.BN = bn;
   p.n_chunks = (p.Nn + bn - 1) / bn;
   p.acc_col0 = u_cols;
-  const int need_cols = cols(bn, p.n_pbuf, p.n_dbuf);
+  const int need_cols = p.d_shared ? u_cols + (p.n_pbuf + 1) * bn : cols(bn, p.n_pbuf, p.n_dbuf);
   MTL_REQUIRE(need_cols <= 512, "linear: TMEM budget exceeded (R_pad=%d, S_out=%d)", p.R_pad, p.S_out);
   p.tmem_cols = 32;
   while (p.tmem_cols < need_cols) p.tmem_cols *= 2;

@@ -38,6 +38,7 @@ struct LinPlan {
   int n_regions;  // 1: dense + adapters merged in one accumulator per item; > 1: dense P + per-stream delta D
   int n_pbuf;     // dense accumulator buffers P (multi mode): 2, or 1 when the rank space leaves no room
   int n_dbuf;     // item accumulators per epilogue group (2, or 1 when TMEM is short)
+  int d_shared;   // multi mode, one output stream: a single delta accumulator shared by both epilogue groups
   int n_work;     // work items = row tiles x column splits (walked by persistent CTAs)
   int n_slabs;    // per-epilogue-warp store slabs in shared memory
   int acc_col0;   // first accumulator column in TMEM
