@@ -56,6 +56,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--profile-ops", default="", help="write the per-C-ABI-call CUDA-event profile to this JSON file")
+    ap.add_argument("--ncu-range", action="store_true",
+                    help="profiling aid: after the warm-up run ONE step between cudaProfilerStart/Stop and exit "
+                         "(use with `ncu --profile-from-start off`); prints no bench line")
     return ap.parse_args()
 
 
@@ -307,6 +310,13 @@ def run_ours(a):
     # warm-up (also stages the bf16 copies of the frozen weights)
     for i in range(a.warmup):
         step(resident[i % 2])
+    if a.ncu_range:
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        step(resident[0])
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()

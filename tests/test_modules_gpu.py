@@ -295,6 +295,27 @@ def test_mark_only_lora_and_state_dict(S):
     assert list(new) == ["layers.0.blocks.0.attn.qkv.linear.weight"]
 
 
+def test_patch_embed_autocast_path(S):
+    """PatchEmbed under bf16 autocast (channels-last conv + mtl_layernorm) vs Conv2d + LayerNorm evaluated in fp32
+    (reference swin_transformer_mtlora.py:597-605), forward and the gradients of every trainable parameter."""
+    pe = S.PatchEmbed(img_size=56, patch_size=4, in_chans=3, embed_dim=96, norm_layer=torch.nn.LayerNorm).cuda()
+    load_det(pe, "pe.")
+    x = detgen.uniform("pe.x", (2, 3, 56, 56), -2.0, 2.0).cuda()
+    gy = detgen.uniform("pe.gy", (2, 196, 96)).cuda()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = pe(x)
+    assert y.dtype == torch.bfloat16 and y.shape == (2, 196, 96)
+    (y.float() * gy).sum().backward()
+    got = {n: prm.grad.clone() for n, prm in pe.named_parameters()}
+    for prm in pe.parameters():
+        prm.grad = None
+    ref = torch.nn.functional.layer_norm(pe.proj(x).flatten(2).transpose(1, 2), (96,), pe.norm.weight, pe.norm.bias, 1e-5)
+    (ref * gy).sum().backward()
+    close(y, ref, TOL, "patch_embed y")
+    for n, prm in pe.named_parameters():
+        close(got[n], prm.grad, TOL_PARAM, f"patch_embed d{n}")
+
+
 def test_cpu_tensors_raise(S):
     net = build_c1(S)
     with pytest.raises(RuntimeError):

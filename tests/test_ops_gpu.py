@@ -233,6 +233,27 @@ def test_xty(ops):
     check(C, 0.5 * P.float().t() @ Q.float(), tol=2e-3, what="xty")
 
 
+# alpha == 1 takes the tcgen05 reduction (xty_sm100.cu): MN-major operands, 128-column tiles of the wider matrix
+# (shifted last tile when the width is not a multiple of 128), 64-column chunks of the narrower one, row splits.
+@pytest.mark.parametrize("M,a,b", [
+    (5000, 192, 384),     # dW of PatchMerging.reduction at stage 0 (wide = Q)
+    (777, 96, 200),       # ragged rows, wide tile shifted left (200 = 128 + 72)
+    (4096, 384, 96),      # wide = P
+    (20000, 24, 96),      # narrow rank operand (24 columns), single partially filled wide tile
+    (64, 128, 128),       # a single pipeline step
+    (130000, 80, 328),    # many row splits; rank range crossing a 64-column chunk boundary
+])
+def test_xty_tensor_core_path(ops, M, a, b):
+    P = bf(dev(detgen.uniform(f"xty2.p.{M}.{a}", (M, a))))
+    Q = bf(dev(detgen.uniform(f"xty2.q.{M}.{b}", (M, b))))
+    C = ops.xty(P, Q)
+    ref = (P.double().t() @ Q.double()).float()
+    check(C, ref, tol=2e-3, what=f"xty umma {M}x{a}x{b}")
+    # accumulation semantics (+=) into an existing buffer
+    C2 = ops.xty(P, Q, out=C.clone())
+    check(C2, 2 * ref, tol=2e-3, what="xty umma accumulate")
+
+
 # ------------------------------------------------------------------------------------------------------------------
 ATTN_CASES = [
     # B, H,  W,  nH, ws, shift
