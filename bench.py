@@ -269,13 +269,24 @@ def run_ours(a):
     resident = [h.to(dev) for h in host]
     h2d_bytes = host[0].numel() * host[0].element_size()
 
+    class MeanSquare(torch.autograd.Function):
+        """mean(x^2) with fp32 accumulation: one reduction kernel forward, one elementwise kernel backward."""
+
+        @staticmethod
+        def forward(ctx, x):
+            ctx.save_for_backward(x)
+            return torch.linalg.vector_norm(x, dtype=torch.float32).square() / x.numel()
+
+        @staticmethod
+        def backward(ctx, g):
+            (x,) = ctx.saved_tensors
+            return x * (g * (2.0 / x.numel())).to(x.dtype)
+
     def step(img):
         with torch.autocast("cuda", dtype=torch.bfloat16):
             stages = net(img, return_stages=True)
-        # sum over stages and tasks of mean(x^2), evaluated as ||x||^2 / numel with fp32 accumulation:
-        # one reduction kernel per output instead of cast + pow + mean
-        loss = sum(torch.linalg.vector_norm(v, dtype=torch.float32).square() / v.numel()
-                   for _, tl in stages for v in tl.values())
+        # backbone loss of SURVEY.md §8d: sum over stages and tasks of mean(x^2)
+        loss = sum(MeanSquare.apply(v) for _, tl in stages for v in tl.values())
         loss.backward()
         reducer.reduce()
         opt.step()

@@ -82,7 +82,6 @@ __global__ void __launch_bounds__(128, 4) win_attn_fwd_kernel(const AttnParams p
   __shared__ __align__(16) __nv_bfloat16 Ks[NP * QS];
   __shared__ __align__(16) __nv_bfloat16 Vs[NP * QS];
   __shared__ float bias_s[225];
-  __shared__ int rows_s[NP];
   __shared__ __align__(8) int reg_s[NP];
 
   const int head = blockIdx.y;
@@ -93,6 +92,7 @@ __global__ void __launch_bounds__(128, 4) win_attn_fwd_kernel(const AttnParams p
   const int n_win = p.B * nW;
   const int tbl = (2 * g.ws - 1) * (2 * g.ws - 1);
   for (int i = threadIdx.x; i < tbl; i += blockDim.x) bias_s[i] = p.rpb[i * p.nH + head];
+  if (threadIdx.x < NP) reg_s[threadIdx.x] = 0;
   const int C3 = 3 * p.C;
   __syncthreads();
   // The (query, key) pairs a thread owns are the same for every window, so the relative-position bias of this head
@@ -117,27 +117,42 @@ __global__ void __launch_bounds__(128, 4) win_attn_fwd_kernel(const AttnParams p
     }
   }
   const float scale2 = p.scale * kLog2e;
+  // gather / scatter ownership: thread t moves the 16-byte chunk (t & 3) of window tokens (t >> 2) and (t >> 2) + 32
+  // of every tile, so the token -> row index math is done twice per window and thread, in registers
+  const int ch8 = (threadIdx.x & 3) * 8;
+  const int tok_a = threadIdx.x >> 2, tok_b = tok_a + 32;
+  const int ay = tok_a / g.ws, ax = tok_a - ay * g.ws, by = tok_b / g.ws, bx = tok_b - by * g.ws;
+  const bool a_ok = tok_a < g.N, b_ok = tok_b < g.N;
+  const uint32_t q_a = smem_u32(Qs + tok_a * QS + ch8), q_b = smem_u32(Qs + tok_b * QS + ch8);
 
   for (int win = blockIdx.x; win < n_win; win += gridDim.x) {
     const int b = win / nW, wi = win - b * nW;
     const int wy = wi / g.nww, wx = wi - wy * g.nww;
     // only windows in the last window row / column straddle the shift seam (:297-319)
     const bool seam = p.mask == nullptr && g.shift > 0 && (wy == g.nwh - 1 || wx == g.nww - 1);
-    __syncthreads();  // previous iteration done with smem
-    if (threadIdx.x < NP) {
-      const int i = threadIdx.x;
-      rows_s[i] = i < g.N ? token_row(g, b, wy, wx, i) : -1;
-      reg_s[i] = (i < g.N && seam) ? region_id(g, wy, wx, i) : 0;
+    int ra, rb;
+    {
+      int r = wy * g.ws + ay + g.shift, c = wx * g.ws + ax + g.shift;
+      if (r >= g.H) r -= g.H;
+      if (c >= g.W) c -= g.W;
+      ra = (b * g.H + r) * g.W + c;
+      r = wy * g.ws + by + g.shift; c = wx * g.ws + bx + g.shift;
+      if (r >= g.H) r -= g.H;
+      if (c >= g.W) c -= g.W;
+      rb = (b * g.H + r) * g.W + c;
     }
-    __syncthreads();
-    // gather q,k,v rows of this head: 3 tiles x 64 rows x 4 chunks of 16 B
-    for (int idx = threadIdx.x; idx < 3 * NP * 4; idx += blockDim.x) {
-      const int which = idx / (NP * 4), rem = idx - which * NP * 4;
-      const int i = rem >> 2, ch = rem & 3;
-      __nv_bfloat16* dst = (which == 0 ? Qs : which == 1 ? Ks : Vs) + i * QS + ch * 8;
-      const int row = rows_s[i];
-      const __nv_bfloat16* src = p.qkv + static_cast<size_t>(row < 0 ? 0 : row) * C3 + which * p.C + head * HD + ch * 8;
-      cp_async_16_zfill(smem_u32(dst), src, row >= 0);
+    __syncthreads();  // previous iteration done with smem
+    if (seam && threadIdx.x < NP) reg_s[threadIdx.x] = threadIdx.x < g.N ? region_id(g, wy, wx, threadIdx.x) : 0;
+    {
+      // gather q,k,v rows of this head: 3 tiles x 2 rows x one 16-byte chunk per thread
+      const __nv_bfloat16* sa = p.qkv + static_cast<size_t>(a_ok ? ra : 0) * C3 + head * HD + ch8;
+      const __nv_bfloat16* sb = p.qkv + static_cast<size_t>(b_ok ? rb : 0) * C3 + head * HD + ch8;
+      cp_async_16_zfill(q_a, sa, a_ok);
+      cp_async_16_zfill(q_b, sb, b_ok);
+      cp_async_16_zfill(smem_u32(Ks + tok_a * QS + ch8), sa + p.C, a_ok);
+      cp_async_16_zfill(smem_u32(Ks + tok_b * QS + ch8), sb + p.C, b_ok);
+      cp_async_16_zfill(smem_u32(Vs + tok_a * QS + ch8), sa + 2 * p.C, a_ok);
+      cp_async_16_zfill(smem_u32(Vs + tok_b * QS + ch8), sb + 2 * p.C, b_ok);
     }
     cp_async_commit();
     cp_async_wait<0>();
@@ -233,12 +248,12 @@ __global__ void __launch_bounds__(128, 4) win_attn_fwd_kernel(const AttnParams p
       *reinterpret_cast<uint32_t*>(Qs + i1 * QS + nt * 8 + t4 * 2) = pack_bf16x2(o[nt][2], o[nt][3]);
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < NP * 4; idx += blockDim.x) {
-      const int i = idx >> 2, ch = idx & 3;
-      const int row = rows_s[i];
-      if (row < 0) continue;
-      const uint4 v = *reinterpret_cast<const uint4*>(Qs + i * QS + ch * 8);
-      const size_t off = static_cast<size_t>(row) * p.C + head * HD + ch * 8;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      if (!(hh ? b_ok : a_ok)) continue;
+      const int i = hh ? tok_b : tok_a;
+      const uint4 v = *reinterpret_cast<const uint4*>(Qs + i * QS + ch8);
+      const size_t off = static_cast<size_t>(hh ? rb : ra) * p.C + head * HD + ch8;
       *reinterpret_cast<uint4*>(p.out + off) = v;
       if (p.out_drop != nullptr) {
         const float keep_scale = 1.f / (1.f - p.drop_p);
@@ -276,7 +291,6 @@ __global__ void __launch_bounds__(128, 3) win_attn_bwd_kernel(const AttnBwdParam
   __shared__ __align__(16) __nv_bfloat16 dSs[NP * PS];
   __shared__ float bias_s[225];
   __shared__ float dbias_s[225];
-  __shared__ int rows_s[NP];
   __shared__ __align__(8) int reg_s[NP];
 
   const int head = blockIdx.y;
@@ -315,33 +329,41 @@ __global__ void __launch_bounds__(128, 3) win_attn_bwd_kernel(const AttnBwdParam
     }
   }
   const float scale2 = p.scale * kLog2e;
+  // gather / scatter ownership as in the forward kernel: chunk (t & 3) of tokens (t >> 2) and (t >> 2) + 32
+  const int ch8 = (threadIdx.x & 3) * 8;
+  const int tok_a = threadIdx.x >> 2, tok_b = tok_a + 32;
+  const int ay = tok_a / g.ws, ax = tok_a - ay * g.ws, by = tok_b / g.ws, bx = tok_b - by * g.ws;
+  const bool a_ok = tok_a < g.N, b_ok = tok_b < g.N;
 
   for (int win = blockIdx.x; win < n_win; win += gridDim.x) {
     const int b = win / nW, wi = win - b * nW;
     const int wy = wi / g.nww, wx = wi - wy * g.nww;
     const bool seam = p.mask == nullptr && g.shift > 0 && (wy == g.nwh - 1 || wx == g.nww - 1);
-    __syncthreads();
-    if (threadIdx.x < NP) {
-      const int i = threadIdx.x;
-      rows_s[i] = i < g.N ? token_row(g, b, wy, wx, i) : -1;
-      reg_s[i] = (i < g.N && seam) ? region_id(g, wy, wx, i) : 0;
+    int ra, rb;
+    {
+      int r = wy * g.ws + ay + g.shift, c = wx * g.ws + ax + g.shift;
+      if (r >= g.H) r -= g.H;
+      if (c >= g.W) c -= g.W;
+      ra = (b * g.H + r) * g.W + c;
+      r = wy * g.ws + by + g.shift; c = wx * g.ws + bx + g.shift;
+      if (r >= g.H) r -= g.H;
+      if (c >= g.W) c -= g.W;
+      rb = (b * g.H + r) * g.W + c;
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < 4 * NP * 4; idx += blockDim.x) {
-      const int which = idx / (NP * 4), rem = idx - which * NP * 4;
-      const int i = rem >> 2, ch = rem & 3;
-      const int row = rows_s[i];
-      const size_t r = static_cast<size_t>(row < 0 ? 0 : row);
-      __nv_bfloat16* dst;
-      const __nv_bfloat16* src;
-      if (which < 3) {
-        dst = (which == 0 ? Qs : which == 1 ? Ks : Vs) + i * QS + ch * 8;
-        src = p.qkv + r * C3 + which * p.C + head * HD + ch * 8;
-      } else {
-        dst = dOs + i * QS + ch * 8;
-        src = p.dout + r * p.C + head * HD + ch * 8;
-      }
-      cp_async_16_zfill(smem_u32(dst), src, row >= 0);
+    if (seam && threadIdx.x < NP) reg_s[threadIdx.x] = threadIdx.x < g.N ? region_id(g, wy, wx, threadIdx.x) : 0;
+    {
+      const size_t oa = static_cast<size_t>(a_ok ? ra : 0), ob = static_cast<size_t>(b_ok ? rb : 0);
+      const __nv_bfloat16* sa = p.qkv + oa * C3 + head * HD + ch8;
+      const __nv_bfloat16* sb = p.qkv + ob * C3 + head * HD + ch8;
+      cp_async_16_zfill(smem_u32(Qs + tok_a * QS + ch8), sa, a_ok);
+      cp_async_16_zfill(smem_u32(Qs + tok_b * QS + ch8), sb, b_ok);
+      cp_async_16_zfill(smem_u32(Ks + tok_a * QS + ch8), sa + p.C, a_ok);
+      cp_async_16_zfill(smem_u32(Ks + tok_b * QS + ch8), sb + p.C, b_ok);
+      cp_async_16_zfill(smem_u32(Vs + tok_a * QS + ch8), sa + 2 * p.C, a_ok);
+      cp_async_16_zfill(smem_u32(Vs + tok_b * QS + ch8), sb + 2 * p.C, b_ok);
+      cp_async_16_zfill(smem_u32(dOs + tok_a * QS + ch8), p.dout + oa * p.C + head * HD + ch8, a_ok);
+      cp_async_16_zfill(smem_u32(dOs + tok_b * QS + ch8), p.dout + ob * p.C + head * HD + ch8, b_ok);
     }
     cp_async_commit();
     cp_async_wait<0>();
@@ -480,14 +502,14 @@ __global__ void __launch_bounds__(128, 3) win_attn_bwd_kernel(const AttnBwdParam
       *reinterpret_cast<uint32_t*>(Vs + i1 * QS + col) = pack_bf16x2(dv[nt][2], dv[nt][3]);
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < 3 * NP * 4; idx += blockDim.x) {
-      const int which = idx / (NP * 4), rem = idx - which * NP * 4;
-      const int i = rem >> 2, ch = rem & 3;
-      const int row = rows_s[i];
-      if (row < 0) continue;
-      const __nv_bfloat16* src = (which == 0 ? Qs : which == 1 ? Ks : Vs) + i * QS + ch * 8;
-      *reinterpret_cast<uint4*>(p.dqkv + static_cast<size_t>(row) * C3 + which * p.C + head * HD + ch * 8) =
-          *reinterpret_cast<const uint4*>(src);
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      if (!(hh ? b_ok : a_ok)) continue;
+      const int i = hh ? tok_b : tok_a;
+      __nv_bfloat16* dst = p.dqkv + static_cast<size_t>(hh ? rb : ra) * C3 + head * HD + ch8;
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(Qs + i * QS + ch8);
+      *reinterpret_cast<uint4*>(dst + p.C) = *reinterpret_cast<const uint4*>(Ks + i * QS + ch8);
+      *reinterpret_cast<uint4*>(dst + 2 * p.C) = *reinterpret_cast<const uint4*>(Vs + i * QS + ch8);
     }
   }
 
