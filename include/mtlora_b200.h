@@ -29,7 +29,7 @@ extern "C" {
 typedef void* mtl_stream_t; /* cudaStream_t */
 
 enum { MTL_MODE_MATRIX = 0 }; /* MTLoRALinear shared_mode 'matrix' (models/lora.py:259-266) */
-enum { MTL_ACT_NONE = 0, MTL_ACT_GELU = 1 };
+enum { MTL_ACT_NONE = 0, MTL_ACT_GELU = 1, MTL_ACT_GELU_GRAD = 2 };
 
 int mtl_abi_version(void);
 const char* mtl_last_error(void);
@@ -54,6 +54,8 @@ typedef struct mtl_linear_cfg {
   float dropout_p;        /* lora_dropout in training, else 0 */
   uint64_t dropout_seed;  /* counter-based mask seed; same value in forward and backward */
   int32_t rows_per_sample;/* L = H*W: rows of one image, for per-sample DropPath scales (0 = unused) */
+  int32_t gelu_aux_is_grad;/* mtl_linear_bwd_input: gelu_aux already holds GELU'(pre-activation) (the producing layer ran
+                            * with MTL_ACT_GELU_GRAD) -> dx *= gelu_aux instead of dx *= GELU'(gelu_aux) */
 } mtl_linear_cfg;
 
 /* Width R of the packed rank space: every adapter (shared first, then the tasks in module order) starts on a
@@ -84,6 +86,9 @@ int mtl_cast_transpose(const float* w, void* w_bf16, void* wt_bf16, int32_t rows
  * act == MTL_ACT_GELU (Mlp.forward swin_transformer_mtlora.py:69-75): y keeps the pre-activation (needed by
  *        backward), y_act [1+T (+1 if dropout_p > 0), M, N] receives GELU(y) and, last, D(GELU(y[0])) drawn with
  *        dropout_seed + 1 (the seed the consuming fc2 layer must be called with).
+ * act == MTL_ACT_GELU_GRAD: as MTL_ACT_GELU, but y receives GELU'(pre-activation) = Phi(y) + y pdf(y) (evaluated on
+ *        the fp32 accumulator) — all the backward of the consuming layer needs (cfg.gelu_aux_is_grad = 1), which
+ *        turns its epilogue into one multiply per element.
  * residual/res_streams/path_scale (SwinTransformerBlock.forward :389-392,398-408): when residual != NULL,
  *        y[j] = residual[res_streams == 1 ? 0 : j] + path_scale[j, sample] * (above); path_scale may be NULL (=1),
  *        layout [1+T, M / rows_per_sample] fp32 (DropPath keep-mask / keep-prob, independent per stream).

@@ -9,7 +9,7 @@ import os
 MTL_MAX_TASKS = 7
 MTL_ABI_VERSION = 1
 MTL_MODE_MATRIX = 0
-MTL_ACT_NONE, MTL_ACT_GELU = 0, 1
+MTL_ACT_NONE, MTL_ACT_GELU, MTL_ACT_GELU_GRAD = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmtlora_b200.so")
@@ -34,6 +34,7 @@ class LinearCfg(ctypes.Structure):
         ("dropout_p", c_float),
         ("dropout_seed", c_uint64),
         ("rows_per_sample", c_int32),
+        ("gelu_aux_is_grad", c_int32),
     ]
 
 

@@ -164,8 +164,9 @@ int mtl_linear_fwd(const mtl_linear_cfg* cfg, const void* x, const void* w_bf16,
   if (int e = check_ptr16(w_bf16, "linear_fwd: w_bf16")) return e;
   if (int e = check_ptr16(y, "linear_fwd: y")) return e;
   MTL_REQUIRE(cfg->M > 0 && cfg->M < (1ll << 31), "linear_fwd: M=%lld out of range", (long long)cfg->M);
-  MTL_REQUIRE(act == MTL_ACT_NONE || act == MTL_ACT_GELU, "linear_fwd: unknown activation %d", act);
-  MTL_REQUIRE(act != MTL_ACT_GELU || y_act != nullptr, "linear_fwd: y_act required with MTL_ACT_GELU");
+  MTL_REQUIRE(act == MTL_ACT_NONE || act == MTL_ACT_GELU || act == MTL_ACT_GELU_GRAD, "linear_fwd: unknown activation %d",
+              act);
+  MTL_REQUIRE(act == MTL_ACT_NONE || y_act != nullptr, "linear_fwd: y_act required with MTL_ACT_GELU / MTL_ACT_GELU_GRAD");
   MTL_REQUIRE(cfg->dropout_p >= 0.f && cfg->dropout_p < 1.f, "dropout probability has to be in [0, 1), but got %f",
               cfg->dropout_p);
   const int T = cfg->n_tasks;
@@ -210,7 +211,7 @@ int mtl_linear_fwd(const mtl_linear_cfg* cfg, const void* x, const void* w_bf16,
       p.out_len[j][0] = L.len[j];
     }
   }
-  p.ep_mode = (act == MTL_ACT_GELU) ? LIN_EP_GELU_DUAL : LIN_EP_NONE;
+  p.ep_mode = act == MTL_ACT_GELU ? LIN_EP_GELU_DUAL : act == MTL_ACT_GELU_GRAD ? LIN_EP_GELU_DUAL_GRAD : LIN_EP_NONE;
   p.bias = bias;
   p.y = static_cast<__nv_bfloat16*>(y);
   p.y2 = static_cast<__nv_bfloat16*>(y_act);
@@ -227,7 +228,7 @@ int mtl_linear_fwd(const mtl_linear_cfg* cfg, const void* x, const void* w_bf16,
     p.n_samples = static_cast<int>(cfg->M / cfg->rows_per_sample);
   }
   p.u_save = static_cast<__nv_bfloat16*>(u_save);
-  if (drop && act == MTL_ACT_GELU) p.drop_mode = 1;
+  if (drop && act != MTL_ACT_NONE) p.drop_mode = 1;
   p.drop_p = cfg->dropout_p;
   p.drop_seed = cfg->dropout_seed;
   return launch_linear(p, x, w_bf16, a_cat, b_cat, S(stream));
@@ -283,7 +284,7 @@ int mtl_linear_bwd_input(const mtl_linear_cfg* cfg, const void* dy, const void* 
       p.out_len[1 + t][0] = L.len[1 + t];
     }
   }
-  p.ep_mode = gelu_aux != nullptr ? LIN_EP_GELU_BWD : LIN_EP_NONE;
+  p.ep_mode = gelu_aux == nullptr ? LIN_EP_NONE : (cfg->gelu_aux_is_grad ? LIN_EP_MUL_AUX : LIN_EP_GELU_BWD);
   p.aux = static_cast<const __nv_bfloat16*>(gelu_aux);
   p.y = static_cast<__nv_bfloat16*>(dx);
   if (path_scale != nullptr) {

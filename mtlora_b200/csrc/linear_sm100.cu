@@ -166,6 +166,24 @@ __device__ __forceinline__ void gelu16_pack(const float (&v)[16], uint32_t (&pk)
     pk[i] = pack_bf16x2(g0, g1);
   }
 }
+// GELU(v) and GELU'(v) = Phi(v) + v * pdf(v) for a granule, both packed to bf16x2 (fc1 forward when the consuming
+// fc2 backward wants the derivative factor instead of the pre-activation)
+__device__ __forceinline__ void gelu_and_grad16_pack(const float (&v)[16], uint32_t (&pk_gelu)[8], uint32_t (&pk_grad)[8]) {
+  uint64_t phi[8];
+  phi16(v, phi);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float g0, g1, d0, d1;
+    const uint64_t v2 = pack2(v[2 * i], v[2 * i + 1]);
+    unpack2(mul2(v2, phi[i]), g0, g1);
+    pk_gelu[i] = pack_bf16x2(g0, g1);
+    // pdf = exp(-x^2 / 2) / sqrt(2 pi); for |x| > 4 both x * pdf and the clamping error of Phi are < 6e-4
+    const float p0 = 0.39894228040143267794f * ex2_approx(-0.72134752044448170368f * v[2 * i] * v[2 * i]);
+    const float p1 = 0.39894228040143267794f * ex2_approx(-0.72134752044448170368f * v[2 * i + 1] * v[2 * i + 1]);
+    unpack2(fma2(v2, pack2(p0, p1), phi[i]), d0, d1);
+    pk_grad[i] = pack_bf16x2(d0, d1);
+  }
+}
 // v *= GELU'(a) for a granule; a given as 8 packed bf16x2 words. GELU'(x) = Phi(x) + x * pdf(x)
 __device__ __forceinline__ void gelu_grad16_mul(float (&v)[16], const uint32_t (&aw)[8]) {
   float a[16];
@@ -545,7 +563,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const uint32_t thr = dropout_threshold(p.drop_p);
     const float keep_scale = 1.f / (1.f - p.drop_p);
     const size_t stream_stride = static_cast<size_t>(p.M) * p.Nn;
-    constexpr bool dual = EP == LIN_EP_GELU_DUAL;
+    constexpr bool dual = EP == LIN_EP_GELU_DUAL || EP == LIN_EP_GELU_DUAL_GRAD;
 
     uint32_t lw = 0, Cn = 0, G = 0;
     Tracer<TRACE> tr;
@@ -608,7 +626,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           // Epilogue inputs that do not depend on the accumulators (the GELU' argument of the fc2 backward, the residual
           // of proj / fc2 forward) are staged by TMA into the very slab the half's output will be written to, one
           // 64-column half ahead (across item and tile boundaries), so their HBM latency never stalls the math.
-          constexpr bool need_aux = EP == LIN_EP_GELU_BWD, need_res = HAS_RES;
+          constexpr bool need_aux = EP == LIN_EP_GELU_BWD || EP == LIN_EP_MUL_AUX, need_res = HAS_RES;
           constexpr bool has_in = need_aux || need_res;
           int nx_w = w, nx_ci = ci, nx_j = j;      // lookahead: this group's next item
           bool nx_valid = true;
@@ -740,14 +758,31 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               float v[16];
 #pragma unroll
               for (int i = 0; i < 8; ++i) unpack2(v2[i], v[2 * i], v[2 * i + 1]);
-              if (need_aux) gelu_grad16_mul(v, aw);
-              uint32_t pk[8];
+              if (EP == LIN_EP_GELU_BWD) gelu_grad16_mul(v, aw);
+              if (EP == LIN_EP_MUL_AUX) {   // aux already holds GELU'(pre-activation)
 #pragma unroll
-              for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+                for (int i = 0; i < 8; ++i) {
+                  v[2 * i] *= bf16lo_to_f32(aw[i]);
+                  v[2 * i + 1] *= bf16hi_to_f32(aw[i]);
+                }
+              }
+              uint32_t pk[8];
+              [[maybe_unused]] uint32_t pk_act[8];
+              if (EP == LIN_EP_GELU_DUAL_GRAD) {
+                gelu_and_grad16_pack(v, pk_act, pk);   // y <- GELU'(v), y2 <- GELU(v)
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+              }
               *reinterpret_cast<uint4*>(sy + sw64_offset(lane, g2 * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               *reinterpret_cast<uint4*>(sy + sw64_offset(lane, g2 * 16 + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
               if (dual) {
-                gelu16_pack(v, pk);
+                if (EP == LIN_EP_GELU_DUAL_GRAD) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) pk[i] = pk_act[i];
+                } else {
+                  gelu16_pack(v, pk);
+                }
                 *reinterpret_cast<uint4*>(sy2 + sw64_offset(lane, g2 * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 *reinterpret_cast<uint4*>(sy2 + sw64_offset(lane, g2 * 16 + 8)) =
                     make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -900,7 +935,9 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
   const int min_stages = n_uatoms > 0 ? n_uatoms + 2 : 2;
   // epilogues with two outputs per half (GELU pair) or with TMA-staged inputs want a third store slab per warp:
   // with two, every half waits for the bulk store that just left (measured: 12.7 us instead of ~5 us per item)
-  const int want_slabs = (p.ep_mode == LIN_EP_GELU_DUAL || p.ep_mode == LIN_EP_GELU_BWD || p.res != nullptr) ? 3 : 2;
+  const bool ep_dual = p.ep_mode == LIN_EP_GELU_DUAL || p.ep_mode == LIN_EP_GELU_DUAL_GRAD;
+  const bool ep_aux = p.ep_mode == LIN_EP_GELU_BWD || p.ep_mode == LIN_EP_MUL_AUX;
+  const int want_slabs = (ep_dual || ep_aux || p.res != nullptr) ? 3 : 2;
   auto fits_smem = [&](int bn_, int slabs) {   // with the minimum ring depth
     return smem_layout(min_stages, kTileABytes + bn_ * 128, p.R_pad, slabs).total + 1024 <= 227u * 1024;
   };
@@ -1004,8 +1041,8 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
   p.n_work = m_tiles * p.n_splits;
 
   // ---- shared memory: store slabs + U operand + as many ring stages as fit ---------------------------------------
-  const bool has_in = p.ep_mode == LIN_EP_GELU_BWD || p.res != nullptr;   // epilogue inputs staged through the slabs
-  p.n_slabs = (p.ep_mode == LIN_EP_GELU_DUAL || has_in) ? 3 : 2;   // reduced to 2 below when smem is short
+  const bool has_in = ep_aux || p.res != nullptr;   // epilogue inputs staged through the slabs
+  p.n_slabs = (ep_dual || has_in) ? 3 : 2;   // reduced to 2 below when smem is short
   if (smem_layout(min_stages, stage_bytes, p.R_pad, p.n_slabs).total + 1024 > 227u * 1024) p.n_slabs = 2;
   p.n_stages = kMaxStages;
   while (p.n_stages > min_stages &&
@@ -1028,7 +1065,7 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
   // epilogue slabs: [32 rows x 32 columns] pieces, 64-byte swizzle
   constexpr CUtensorMapSwizzle kSw64 = CU_TENSOR_MAP_SWIZZLE_64B;
   if (int e = make_tmap(&tm_y, p.y, p.Nn, p.M, p.S_out, kPieceCols, 32, kSw64)) return e;
-  if (p.ep_mode == LIN_EP_GELU_DUAL) {
+  if (ep_dual) {
     MTL_REQUIRE(p.y2 != nullptr, "linear: GELU epilogue needs y2");
     if (int e = make_tmap(&tm_y2, p.y2, p.Nn, p.M, p.S_out + (p.drop_mode == 1 ? 1 : 0), kPieceCols, 32, kSw64)) return e;
   } else {
@@ -1039,10 +1076,10 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
   } else {
     tm_u = tm_y;
   }
-  MTL_REQUIRE(!(p.ep_mode == LIN_EP_GELU_BWD && p.res != nullptr), "linear: GELU' epilogue cannot take a residual");
+  MTL_REQUIRE(!((ep_aux || ep_dual) && p.res != nullptr), "linear: GELU epilogues cannot take a residual");
   // tm_pf: the same tensor with [128 rows x 64 columns] boxes, used by the producer to prefetch the epilogue inputs
   // of a work item into L2 while its accumulators are still being formed
-  if (p.ep_mode == LIN_EP_GELU_BWD) {
+  if (ep_aux) {
     MTL_REQUIRE(p.aux != nullptr, "linear: GELU' epilogue needs aux");
     if (int e = make_tmap(&tm_in, p.aux, p.Nn, p.M, p.S_out, kPieceCols, 32, kSw64)) return e;
     if (int e = make_tmap(&tm_pf, p.aux, p.Nn, p.M, p.S_out, 64, LIN_BM, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
@@ -1059,24 +1096,24 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
 
   using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
                             CUtensorMap, CUtensorMap, LinPlan);
-  static KernelFn kernels[3][2][2] = {
-      {{mtl_linear_kernel<LIN_EP_NONE, false, false>, mtl_linear_kernel<LIN_EP_NONE, false, true>},
-       {mtl_linear_kernel<LIN_EP_NONE, true, false>, mtl_linear_kernel<LIN_EP_NONE, true, true>}},
-      {{mtl_linear_kernel<LIN_EP_GELU_DUAL, false, false>, mtl_linear_kernel<LIN_EP_GELU_DUAL, false, true>},
-       {mtl_linear_kernel<LIN_EP_GELU_DUAL, true, false>, mtl_linear_kernel<LIN_EP_GELU_DUAL, true, true>}},
-      {{mtl_linear_kernel<LIN_EP_GELU_BWD, false, false>, mtl_linear_kernel<LIN_EP_GELU_BWD, false, true>},
-       {mtl_linear_kernel<LIN_EP_GELU_BWD, true, false>, mtl_linear_kernel<LIN_EP_GELU_BWD, true, true>}}};
+  // [epilogue mode][trace]; the residual variant exists for LIN_EP_NONE only (index 5)
+  static KernelFn kernels[6][2] = {
+      {mtl_linear_kernel<LIN_EP_NONE, false, false>, mtl_linear_kernel<LIN_EP_NONE, false, true>},
+      {mtl_linear_kernel<LIN_EP_GELU_DUAL, false, false>, mtl_linear_kernel<LIN_EP_GELU_DUAL, false, true>},
+      {mtl_linear_kernel<LIN_EP_GELU_BWD, false, false>, mtl_linear_kernel<LIN_EP_GELU_BWD, false, true>},
+      {mtl_linear_kernel<LIN_EP_GELU_DUAL_GRAD, false, false>, mtl_linear_kernel<LIN_EP_GELU_DUAL_GRAD, false, true>},
+      {mtl_linear_kernel<LIN_EP_MUL_AUX, false, false>, mtl_linear_kernel<LIN_EP_MUL_AUX, false, true>},
+      {mtl_linear_kernel<LIN_EP_NONE, true, false>, mtl_linear_kernel<LIN_EP_NONE, true, true>}};
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   static int max_ctas = -1;
   static uint32_t wait_hint = 1000u;
   std::call_once(attr_once, []() {
-    for (int a = 0; a < 3; ++a)
-      for (int b = 0; b < 2; ++b)
-        for (int c = 0; c < 2; ++c) {
-          cudaError_t e = cudaFuncSetAttribute(kernels[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-          if (e != cudaSuccess) attr_err = e;
-        }
+    for (int a = 0; a < 6; ++a)
+      for (int c = 0; c < 2; ++c) {
+        cudaError_t e = cudaFuncSetAttribute(kernels[a][c], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) attr_err = e;
+      }
     const char* e = getenv("MTL_LINEAR_MAX_CTAS");  // debugging aid: 0 = one CTA per work item (non-persistent)
     max_ctas = e ? atoi(e) : -1;
     const char* h = getenv("MTL_WAIT_HINT_NS");      // mbarrier.try_wait suspend-time hint (tuning aid)
@@ -1090,12 +1127,12 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
     MTL_CHECK_CUDA(cudaMalloc(&p.trace, 4 * 2048 * sizeof(unsigned long long)));
     MTL_CHECK_CUDA(cudaMemsetAsync(p.trace, 0, 4 * 2048 * sizeof(unsigned long long), stream));
   }
-  MTL_REQUIRE(p.ep_mode >= 0 && p.ep_mode <= 2, "linear: unknown epilogue mode %d", p.ep_mode);
+  MTL_REQUIRE(p.ep_mode >= 0 && p.ep_mode <= 4, "linear: unknown epilogue mode %d", p.ep_mode);
 
   int grid = p.n_work < n_sm ? p.n_work : n_sm;
   if (max_ctas == 0) grid = p.n_work;
   else if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  kernels[p.ep_mode][p.res != nullptr ? 1 : 0][p.trace != nullptr ? 1 : 0]<<<grid, kThreads, smem_bytes, stream>>>(
+  kernels[p.res != nullptr ? 5 : p.ep_mode][p.trace != nullptr ? 1 : 0]<<<grid, kThreads, smem_bytes, stream>>>(
       tm_x, tm_w, tm_down, tm_up, tm_y, tm_y2, tm_u, tm_in, tm_pf, p);
   note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());

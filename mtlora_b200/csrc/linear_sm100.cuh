@@ -24,6 +24,8 @@ enum LinEpilogue : int {
   LIN_EP_NONE = 0,
   LIN_EP_GELU_DUAL = 1,  // y = v, y2 = gelu(v)                (fc1 forward, Mlp.forward :69-75)
   LIN_EP_GELU_BWD = 2,   // y = v * gelu'(aux)                 (fc2 input-gradient -> d(fc1 out))
+  LIN_EP_GELU_DUAL_GRAD = 3,  // y = gelu'(v), y2 = gelu(v)     (fc1 forward keeping the derivative factor instead of v)
+  LIN_EP_MUL_AUX = 4,    // y = v * aux                        (fc2 input-gradient, aux = gelu'(fc1 out) saved by mode 3)
 };
 
 struct LinPlan {

@@ -87,13 +87,13 @@ class LinearEngine:
         return self._w, self._wt, self._packed
 
     # ---- explicit forward / backward ---------------------------------------------------------------------------
-    def forward(self, x, *, xt=False, gelu=False, residual=None, path_scale=None, rows_per_sample=0, dropout_p=0.0,
-                seed=0, save=True):
+    def forward(self, x, *, xt=False, gelu=False, gelu_grad=False, residual=None, path_scale=None, rows_per_sample=0,
+                dropout_p=0.0, seed=0, save=True):
         """x [S_in, M, K] bf16 (incl. the appended D(x[0]) stream when dropout_p > 0) -> y, y_act, saved-dict."""
         w, _, (a_cat, b_cat, _, _) = self.stage()
         bias = self.linear.bias
         bias = None if bias is None else bias.detach().float()
-        y, y_act, u = ops.linear_fwd(self.spec, x, w, bias, a_cat, b_cat, x_tasks_given=xt, act_gelu=gelu,
+        y, y_act, u = ops.linear_fwd(self.spec, x, w, bias, a_cat, b_cat, x_tasks_given=xt, act_gelu=gelu, gelu_grad=gelu_grad,
                                      residual=residual, path_scale=path_scale, rows_per_sample=rows_per_sample,
                                      dropout_p=dropout_p, seed=seed, save_u=save)
         saved = None
@@ -102,7 +102,7 @@ class LinearEngine:
                          rows_per_sample=rows_per_sample)
         return y, y_act, saved
 
-    def backward(self, saved, dy, *, gelu_aux=None, need_dx=True):
+    def backward(self, saved, dy, *, gelu_aux=None, aux_is_grad=False, need_dx=True):
         """dy [S_out, M, N] -> dx [1 (+T), M, K], {param: fp32 grad} for every parameter that requires grad.
 
         DropPath (`path_scale` given in forward): a single-stream layer scales inside the kernels, a multi-stream
@@ -117,6 +117,7 @@ class LinearEngine:
         ad = self.adapters()
         want_ad = any(p.requires_grad for p in ad)
         dx, g = ops.linear_bwd_input(spec, dy, wt, a_cat_t, b_cat_t, x_tasks_given=saved["xt"], gelu_aux=gelu_aux,
+                                     aux_is_grad=aux_is_grad,
                                      path_scale=ps, rows_per_sample=rps if ps is not None else 0,
                                      dropout_p=saved["dropout_p"], seed=saved["seed"], save_g=want_ad)
         grads = {}

@@ -52,7 +52,7 @@ class LinearSpec:
         self.offsets = [lib.mtl_linear_rank_offset(ctypes.byref(c), i) for i in range(self.S_out if self.r_shared else 0)]
         self.ranks = ([self.r_shared] + self.r_tasks) if self.r_shared else []
 
-    def cfg(self, M, x_tasks_given, dropout_p=0.0, seed=0, rows_per_sample=0):
+    def cfg(self, M, x_tasks_given, dropout_p=0.0, seed=0, rows_per_sample=0, gelu_aux_is_grad=False):
         c = N.LinearCfg()
         c.M = int(M)
         c.in_features, c.out_features = self.K, self.Nf
@@ -67,6 +67,7 @@ class LinearSpec:
         c.dropout_p = float(dropout_p)
         c.dropout_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         c.rows_per_sample = int(rows_per_sample)
+        c.gelu_aux_is_grad = 1 if gelu_aux_is_grad else 0
         return c
 
     def n_in_streams(self, x_tasks_given, dropout_p):
@@ -109,9 +110,12 @@ def pack_adapters(spec, a_shared, b_shared, a_tasks=(), b_tasks=(), fwd=True, bw
 # ----------------------------------------------------------------------------------------------------------------
 # MTLoRALinear
 # ----------------------------------------------------------------------------------------------------------------
-def linear_fwd(spec, x, w_bf16, bias, a_cat, b_cat, *, x_tasks_given=False, act_gelu=False, residual=None,
-               path_scale=None, rows_per_sample=0, dropout_p=0.0, seed=0, save_u=False):
-    """x: [S_in, M, K] -> y [S_out, M, N], y_act (GELU) or None, u_save [M, R] or None."""
+def linear_fwd(spec, x, w_bf16, bias, a_cat, b_cat, *, x_tasks_given=False, act_gelu=False, gelu_grad=False,
+               residual=None, path_scale=None, rows_per_sample=0, dropout_p=0.0, seed=0, save_u=False):
+    """x: [S_in, M, K] -> y [S_out, M, N], y_act (GELU) or None, u_save [M, R] or None.
+
+    act_gelu: y = pre-activation, y_act = GELU(y); with gelu_grad=True y holds GELU'(pre-activation) instead (pass it as
+    `gelu_aux` with aux_is_grad=True to the consuming layer's linear_bwd_input)."""
     _chk(x, BF16, "x"); _chk(w_bf16, BF16, "w_bf16"); _chk(bias, torch.float32, "bias")
     _chk(residual, BF16, "residual"); _chk(path_scale, torch.float32, "path_scale")
     S_in, M, K = x.shape
@@ -130,14 +134,15 @@ def linear_fwd(spec, x, w_bf16, bias, a_cat, b_cat, *, x_tasks_given=False, act_
         res_streams = residual.shape[0]
     c = spec.cfg(M, x_tasks_given, dropout_p, seed, rows_per_sample)
     N.call("mtl_linear_fwd", ctypes.byref(c), N.ptr(x), N.ptr(w_bf16), N.ptr(bias), N.ptr(a_cat), N.ptr(b_cat),
-           N.MTL_ACT_GELU if act_gelu else N.MTL_ACT_NONE, N.ptr(y), N.ptr(y_act), N.ptr(residual), res_streams,
+           (N.MTL_ACT_GELU_GRAD if gelu_grad else N.MTL_ACT_GELU) if act_gelu else N.MTL_ACT_NONE, N.ptr(y), N.ptr(y_act),
+           N.ptr(residual), res_streams,
            N.ptr(path_scale), N.ptr(u), N.stream(),
            meta=("fwd", M, spec.K, spec.Nf, 1 + (spec.T if (x_tasks_given and spec.r_shared > 0) else 0), spec.S_out, spec.R_pad, sum(spec.ranks), bias is not None))
     return y, y_act, u
 
 
-def linear_bwd_input(spec, dy, wt_bf16, a_cat_t, b_cat_t, *, x_tasks_given=False, gelu_aux=None, path_scale=None,
-                     rows_per_sample=0, dropout_p=0.0, seed=0, save_g=False):
+def linear_bwd_input(spec, dy, wt_bf16, a_cat_t, b_cat_t, *, x_tasks_given=False, gelu_aux=None, aux_is_grad=False,
+                     path_scale=None, rows_per_sample=0, dropout_p=0.0, seed=0, save_g=False):
     """dy: [S_out, M, N] -> dx [1 (+T), M, K], g_save [M, R] or None."""
     _chk(dy, BF16, "dy"); _chk(wt_bf16, BF16, "wt_bf16"); _chk(gelu_aux, BF16, "gelu_aux")
     S, M, Nf = dy.shape
@@ -146,7 +151,7 @@ def linear_bwd_input(spec, dy, wt_bf16, a_cat_t, b_cat_t, *, x_tasks_given=False
     xt = x_tasks_given and spec.T > 0
     dx = torch.empty((1 + (spec.T if xt else 0), M, spec.K), dtype=BF16, device=dy.device)
     g = torch.empty((M, spec.R_pad), dtype=BF16, device=dy.device) if (save_g and spec.r_shared > 0) else None
-    c = spec.cfg(M, x_tasks_given, dropout_p, seed, rows_per_sample)
+    c = spec.cfg(M, x_tasks_given, dropout_p, seed, rows_per_sample, gelu_aux_is_grad=aux_is_grad)
     N.call("mtl_linear_bwd_input", ctypes.byref(c), N.ptr(dy), N.ptr(wt_bf16), N.ptr(a_cat_t), N.ptr(b_cat_t),
            N.ptr(dx), N.ptr(gelu_aux), N.ptr(path_scale), N.ptr(g), N.stream(),
            meta=("bwd_input", M, spec.K, spec.Nf, dx.shape[0], S, spec.R_pad, sum(spec.ranks), False))

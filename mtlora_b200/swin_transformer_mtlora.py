@@ -373,7 +373,9 @@ class _BlockFn(torch.autograd.Function):
         xt = S > 1
         # LN2 on every stream (:395-396) (+ D(h2[0]) appended)
         h2, mean2, rstd2 = ops.layernorm_fwd(x1.view(S * M, C), n2w, n2b, eps2, dropout_p=p_fc1, seed=s3, drop_rows=M)
-        g, m, sv_1 = e_fc1.forward(h2.view(-1, M, C), xt=xt, gelu=True, dropout_p=p_fc1, seed=s3, save=need)
+        # g = GELU'(fc1 output) (all the fc2 backward needs of the pre-activation), m = GELU(fc1 output)
+        g, m, sv_1 = e_fc1.forward(h2.view(-1, M, C), xt=xt, gelu=True, gelu_grad=True, dropout_p=p_fc1, seed=s3,
+                                   save=need)
         y, _, sv_2 = e_fc2.forward(m, xt=xt, residual=x1, path_scale=ps2, rows_per_sample=L, dropout_p=p_fc2,
                                    seed=s3 + 1, save=need)
         if need:
@@ -396,7 +398,7 @@ class _BlockFn(torch.autograd.Function):
         dy = _grad_stack(dys, (M, C), sv["x"].device)
         grads = {}
         # fc2 -> d(fc1 pre-activation), GELU' fused into the epilogue
-        dg, g2 = e_fc2.backward(sv["sv_2"], dy, gelu_aux=sv["g"])
+        dg, g2 = e_fc2.backward(sv["sv_2"], dy, gelu_aux=sv["g"], aux_is_grad=True)
         if dys[0] is None and S > 1 and e_fc2.spec.r_shared > 0:
             # the shared output stream is unused downstream (last stage, reference quirk: its fc2.lora_shared_{A,B}
             # receive no gradient at all) -> report None like autograd does, not zeros

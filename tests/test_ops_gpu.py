@@ -193,6 +193,36 @@ def test_linear_gelu_bwd_aux(ops):
     check(dx, pre.grad, what="d pre-activation")
 
 
+def test_linear_gelu_grad_factor(ops):
+    """MTL_ACT_GELU_GRAD: fc1 keeps GELU'(pre-activation) instead of the pre-activation, and the consuming fc2 input
+    gradient multiplies by it (cfg.gelu_aux_is_grad) — same result as differentiating GELU (Mlp.forward :69-77)."""
+    M, K, N = 392, 96, 384
+    spec, p, tasks, tscale = make_layer(ops, "gg1", K, N, 64, [4, 4])
+    wb, wt, a_cat, b_cat, a_cat_t, b_cat_t = pack(ops, spec, p, tasks)
+    x = bf(dev(detgen.uniform("gg.x", (3, M, K), -2.0, 2.0)))
+    yg, y_act, _ = ops.linear_fwd(spec, x, wb, p.get("linear.bias"), a_cat, b_cat, x_tasks_given=True, act_gelu=True,
+                                  gelu_grad=True)
+    xf = x.float()
+    pre, act, _ = ref_linear(p, tasks, tscale, xf[0], {t: xf[1 + i] for i, t in enumerate(tasks)}, True, None, None, M)
+    cdf = 0.5 * (1.0 + torch.erf(pre * 0.7071067811865476))
+    pdf = 0.3989422804014327 * torch.exp(-0.5 * pre * pre)
+    check(yg, cdf + pre * pdf, what="GELU' factor")
+    check(y_act, act, what="gelu")
+    # consuming layer (fc2): dx = (dy W + ...) * factor
+    spec2, p2, tasks2, tscale2 = make_layer(ops, "gg2", N, K, 64, [4, 4])
+    wb2, wt2, a2, b2, a2t, b2t = pack(ops, spec2, p2, tasks2)
+    g_pre = bf(dev(detgen.uniform("gg.pre", (3, M, N), -3.0, 3.0)))
+    dy = bf(dev(detgen.uniform("gg.dy", (3, M, K))))
+    pre2 = g_pre.float().requires_grad_()
+    h = torch.nn.functional.gelu(pre2)
+    y, yt = O.mtlora_linear(p2, "", h[0], {t: h[1 + i] for i, t in enumerate(tasks2)}, tasks2, 4.0, tscale2)
+    (torch.stack([y] + [yt[t] for t in tasks2]) * dy.float()).sum().backward()
+    gf = g_pre.float()
+    factor = bf(0.5 * (1.0 + torch.erf(gf * 0.7071067811865476)) + gf * 0.3989422804014327 * torch.exp(-0.5 * gf * gf))
+    dx, _ = ops.linear_bwd_input(spec2, dy, wt2, a2t, b2t, x_tasks_given=True, gelu_aux=factor, aux_is_grad=True)
+    check(dx, pre2.grad, what="d pre-activation (factor)")
+
+
 def test_linear_dropout_stream(ops):
     """LoRA dropout (lora.py:258): adapters of the shared input read D(x), the frozen product reads x."""
     M, K, N, p_drop, seed = 392, 96, 96, 0.25, 1234

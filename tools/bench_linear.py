@@ -53,7 +53,7 @@ def main():
     S_out = spec.S_out
 
     if kind in ("fc1", "fc1_single"):
-        fn = lambda: ops.linear_fwd(spec, x, wb, bias, a_cat, b_cat, x_tasks_given=xt, act_gelu=True, dropout_p=p, seed=1, save_u=True)
+        fn = lambda: ops.linear_fwd(spec, x, wb, bias, a_cat, b_cat, x_tasks_given=xt, act_gelu=True, gelu_grad=True, dropout_p=p, seed=1, save_u=True)
         meta = ("fwd", M, K, N, 1 + (T if xt else 0), S_out, spec.R_pad, sum(spec.ranks), True)
     elif kind in ("fc2", "proj", "qkv"):
         res = torch.randn(S_out if kind == "fc2" else 1, M, N, device=dev, generator=g).to(BF) if kind != "qkv" else None
@@ -65,7 +65,7 @@ def main():
         dy = torch.randn(S_out, M, N, device=dev, generator=g).to(BF)
         n_dx = 1 + (T if xt else 0)
         aux = torch.randn(n_dx, M, K, device=dev, generator=g).to(BF) if kind.startswith("fc2_bwd") else None
-        fn = lambda: ops.linear_bwd_input(spec, dy, wt, a_cat_t, b_cat_t, x_tasks_given=xt, gelu_aux=aux, dropout_p=p, seed=1, save_g=True)
+        fn = lambda: ops.linear_bwd_input(spec, dy, wt, a_cat_t, b_cat_t, x_tasks_given=xt, gelu_aux=aux, aux_is_grad=True, dropout_p=p, seed=1, save_g=True)
         meta = ("bwd_input", M, K, N, n_dx, S_out, spec.R_pad, sum(spec.ranks), False)
     for _ in range(3):
         fn()
