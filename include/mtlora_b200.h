@@ -56,6 +56,9 @@ typedef struct mtl_linear_cfg {
   int32_t rows_per_sample;/* L = H*W: rows of one image, for per-sample DropPath scales (0 = unused) */
   int32_t gelu_aux_is_grad;/* mtl_linear_bwd_input: gelu_aux already holds GELU'(pre-activation) (the producing layer ran
                             * with MTL_ACT_GELU_GRAD) -> dx *= gelu_aux instead of dx *= GELU'(gelu_aux) */
+  int32_t dy_has_sum;     /* mtl_linear_bwd_input, layers with task streams: dy holds 1+T+1 streams, the last one being
+                           * sum_j dy[j] (mtl_scale_rows_sum) — the frozen product then reads ONE stream per column
+                           * chunk instead of re-summing the 1+T streams on the tensor cores */
 } mtl_linear_cfg;
 
 /* Width R of the packed rank space: every adapter (shared first, then the tasks in module order) starts on a
@@ -177,6 +180,10 @@ int mtl_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
 int mtl_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, mtl_stream_t stream);
 int mtl_scale_rows(const void* x, const float* scale, void* y, int32_t S, int64_t M, int32_t C,
                    int32_t rows_per_sample, mtl_stream_t stream);
+/* y[s] = x[s] * scale[s, sample] for s < S (scale NULL: plain copy, skipped when y == x) and y[S] = sum_s y[s];
+ * y: [S+1, M, C]. DropPath backward pre-scale fused with the stream sum mtl_linear_bwd_input(dy_has_sum) consumes. */
+int mtl_scale_rows_sum(const void* x, const float* scale, void* y, int32_t S, int64_t M, int32_t C,
+                       int32_t rows_per_sample, mtl_stream_t stream);
 int mtl_add(const void* a, const void* b, void* out, int64_t n, mtl_stream_t stream);
 /* out[i] = sum_{s<S} x[s, i] (+ extra[i] if extra != NULL): gradient of a tensor consumed by S residual streams
  * (shortcut + drop_path(stream), swin_transformer_mtlora.py:389-392). */

@@ -35,6 +35,7 @@ class LinearCfg(ctypes.Structure):
         ("dropout_seed", c_uint64),
         ("rows_per_sample", c_int32),
         ("gelu_aux_is_grad", c_int32),
+        ("dy_has_sum", c_int32),
     ]
 
 
@@ -75,6 +76,7 @@ SIGNATURES = {
     "mtl_dropout": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_uint64, c_void_p]),
     "mtl_scale_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int32, c_void_p]),
     "mtl_add": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "mtl_scale_rows_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int32, c_void_p]),
     "mtl_sum_streams": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p]),
 }
 

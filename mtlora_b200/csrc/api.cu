@@ -257,7 +257,8 @@ int mtl_linear_bwd_input(const mtl_linear_cfg* cfg, const void* dy, const void* 
   p.M = static_cast<int>(cfg->M);
   p.Kc = cfg->out_features;  // contraction runs over the layer's outputs
   p.Nn = cfg->in_features;
-  p.S_in = out_streams(cfg);
+  const bool dy_sum = cfg->dy_has_sum != 0 && out_streams(cfg) > 1;
+  p.S_in = out_streams(cfg) + (dy_sum ? 1 : 0);
   p.S_out = xt ? 1 + T : 1;
   p.R_pad = L.R_pad;
   int adapter_in[1 + MTL_MAX_TASKS] = {0};
@@ -268,8 +269,13 @@ int mtl_linear_bwd_input(const mtl_linear_cfg* cfg, const void* dy, const void* 
     }
     fill_granules(p, L, adapter_in);
   }
-  p.n_main = p.S_in;  // dPre = sum_j dy[j]  (pretrained feeds every output stream, lora.py:262-266,284)
-  for (int j = 0; j < p.S_in; ++j) p.main_in[j] = j;
+  if (dy_sum) {   // the caller appended sum_j dy[j] as the last stream: the frozen product reads one stream, not 1+T
+    p.n_main = 1;
+    p.main_in[0] = p.S_in - 1;
+  } else {
+    p.n_main = p.S_in;  // dPre = sum_j dy[j]  (pretrained feeds every output stream, lora.py:262-266,284)
+    for (int j = 0; j < p.S_in; ++j) p.main_in[j] = j;
+  }
   if (!xt) {
     p.out_useP[0] = 1;
     p.out_r0[0][0] = 0;
@@ -288,7 +294,7 @@ int mtl_linear_bwd_input(const mtl_linear_cfg* cfg, const void* dy, const void* 
   p.aux = static_cast<const __nv_bfloat16*>(gelu_aux);
   p.y = static_cast<__nv_bfloat16*>(dx);
   if (path_scale != nullptr) {
-    MTL_REQUIRE(p.S_in == 1, "linear_bwd_input: in-kernel path_scale needs a single dy stream; pre-scale dy instead");
+    MTL_REQUIRE(out_streams(cfg) == 1, "linear_bwd_input: in-kernel path_scale needs a single dy stream; pre-scale dy instead");
     MTL_REQUIRE(cfg->rows_per_sample > 0 && cfg->M % cfg->rows_per_sample == 0,
                 "linear_bwd_input: rows_per_sample=%d does not divide M=%lld", cfg->rows_per_sample, (long long)cfg->M);
     // a single stream: scaling the rows of dy == scaling the rows of the result. The saved G stays unscaled;
@@ -470,6 +476,11 @@ int mtl_scale_rows(const void* x, const float* scale, void* y, int32_t Sn, int64
                    int32_t rows_per_sample, mtl_stream_t stream) {
   MTL_REQUIRE(x != nullptr && y != nullptr && scale != nullptr, "scale_rows: NULL argument");
   return launch_scale_rows(x, scale, y, Sn, M, C, rows_per_sample, S(stream));
+}
+int mtl_scale_rows_sum(const void* x, const float* scale, void* y, int32_t Sn, int64_t M, int32_t C,
+                       int32_t rows_per_sample, mtl_stream_t stream) {
+  MTL_REQUIRE(x != nullptr && y != nullptr, "scale_rows_sum: NULL argument");
+  return launch_scale_rows_sum(x, scale, y, Sn, M, C, rows_per_sample, S(stream));
 }
 int mtl_add(const void* a, const void* b, void* out, int64_t n, mtl_stream_t stream) {
   MTL_REQUIRE(a != nullptr && b != nullptr && out != nullptr, "add: NULL argument");

@@ -34,6 +34,9 @@ int launch_dropout(const void* x, void* y, long n, float p, uint64_t seed, cudaS
 // y[s, m, :] = x[s, m, :] * scale[s, m / rows_per_sample]   (DropPath gradient pre-scale)
 int launch_scale_rows(const void* x, const float* scale, void* y, int S, long M, int C, int rows_per_sample,
                       cudaStream_t stream);
+// y[s] = x[s] * scale[s, sample] for s < S (scale null: copy, skipped when y == x) and y[S] = sum_s y[s]
+int launch_scale_rows_sum(const void* x, const float* scale, void* y, int S, long M, int C, int rows_per_sample,
+                          cudaStream_t stream);
 // out[i] = sum_{s<S} x[s, i] (+ extra[i] when extra != null), bf16 in/out, fp32 accumulation
 int launch_sum_streams(const void* x, const void* extra, void* out, int S, long n, cudaStream_t stream);
 // out = a + b (bf16)

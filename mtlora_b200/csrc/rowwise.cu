@@ -546,6 +546,41 @@ __global__ void scale_rows_kernel(const __nv_bfloat16* __restrict__ x, const flo
   }
 }
 
+// y[s] = x[s] * scale[s, sample] (scale == null: y[s] = x[s], not rewritten when y == x) and y[S] = sum_s y[s]
+// (sum of the bf16-rounded scaled rows, fp32 accumulation): the pre-summed gradient stream of mtl_linear_bwd_input.
+__global__ void scale_rows_sum_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
+                                      __nv_bfloat16* __restrict__ y, int S, long M, int CV, int rows_per_sample,
+                                      int n_samples) {
+  const long per = M * CV;
+  for (long v = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; v < per;
+       v += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long m = v / CV;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < S; ++s) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(x) + s * per + v);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+      uint32_t o[4];
+      if (scale != nullptr) {
+        const float f = scale[s * n_samples + m / rows_per_sample];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = pack_bf16x2(bf16lo_to_f32(w[e]) * f, bf16hi_to_f32(w[e]) * f);
+        reinterpret_cast<uint4*>(y)[s * per + v] = make_uint4(o[0], o[1], o[2], o[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = w[e];
+        if (y != x) reinterpret_cast<uint4*>(y)[s * per + v] = q;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc[2 * e] += bf16lo_to_f32(o[e]);
+        acc[2 * e + 1] += bf16hi_to_f32(o[e]);
+      }
+    }
+    reinterpret_cast<uint4*>(y)[S * per + v] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                                         pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
 __global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                            __nv_bfloat16* __restrict__ out, long n8) {
   for (long v = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; v < n8;
@@ -760,6 +795,20 @@ int launch_scale_rows(const void* x, const float* scale, void* y, int S, long M,
   scale_rows_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), scale,
                                                              static_cast<__nv_bfloat16*>(y), S, M, C / 8,
                                                              rows_per_sample, static_cast<int>(M / rows_per_sample)); note_launch();
+  MTL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_scale_rows_sum(const void* x, const float* scale, void* y, int S, long M, int C, int rows_per_sample,
+                          cudaStream_t stream) {
+  MTL_REQUIRE(C % 8 == 0 && S >= 1, "scale_rows_sum: bad shape");
+  MTL_REQUIRE(scale == nullptr || (rows_per_sample > 0 && M % rows_per_sample == 0), "scale_rows_sum: bad rows_per_sample");
+  const long per = M * (C / 8);
+  if (per == 0) return 0;
+  const int rps = rows_per_sample > 0 ? rows_per_sample : 1;
+  scale_rows_sum_kernel<<<grid_for(per, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), scale,
+                                                               static_cast<__nv_bfloat16*>(y), S, M, C / 8, rps,
+                                                               static_cast<int>(M / rps)); note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -110,14 +110,21 @@ class LinearEngine:
         spec = self.spec
         _, wt, (_, _, a_cat_t, b_cat_t) = self.stage()
         ps, rps = saved["path_scale"], saved["rows_per_sample"]
-        if ps is not None and spec.S_out > 1:
-            dy = ops.scale_rows(dy, ps, rps)
+        dy_in, dy_sum = dy, False
+        if 1 < spec.S_out < 8 and (ps is not None or spec.K >= 2 * spec.Nf):
+            # hand the kernel sum_j dy[j] as one extra stream so the frozen product streams one operand tile per column
+            # chunk instead of 1+T: worth a pass of its own when there are many chunks (fc2: K = 4 N), free when the
+            # DropPath pre-scale pass is needed anyway (it writes the sum along)
+            dy_in = ops.scale_rows_sum(dy, ps, rps)
+            dy, dy_sum, ps = dy_in[:spec.S_out], True, None
+        elif ps is not None and spec.S_out > 1:
+            dy = dy_in = ops.scale_rows(dy, ps, rps)
             ps = None
         lin = self.linear
         ad = self.adapters()
         want_ad = any(p.requires_grad for p in ad)
-        dx, g = ops.linear_bwd_input(spec, dy, wt, a_cat_t, b_cat_t, x_tasks_given=saved["xt"], gelu_aux=gelu_aux,
-                                     aux_is_grad=aux_is_grad,
+        dx, g = ops.linear_bwd_input(spec, dy_in, wt, a_cat_t, b_cat_t, x_tasks_given=saved["xt"], gelu_aux=gelu_aux,
+                                     aux_is_grad=aux_is_grad, dy_has_sum=dy_sum,
                                      path_scale=ps, rows_per_sample=rps if ps is not None else 0,
                                      dropout_p=saved["dropout_p"], seed=saved["seed"], save_g=want_ad)
         grads = {}

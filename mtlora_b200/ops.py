@@ -52,7 +52,7 @@ class LinearSpec:
         self.offsets = [lib.mtl_linear_rank_offset(ctypes.byref(c), i) for i in range(self.S_out if self.r_shared else 0)]
         self.ranks = ([self.r_shared] + self.r_tasks) if self.r_shared else []
 
-    def cfg(self, M, x_tasks_given, dropout_p=0.0, seed=0, rows_per_sample=0, gelu_aux_is_grad=False):
+    def cfg(self, M, x_tasks_given, dropout_p=0.0, seed=0, rows_per_sample=0, gelu_aux_is_grad=False, dy_has_sum=False):
         c = N.LinearCfg()
         c.M = int(M)
         c.in_features, c.out_features = self.K, self.Nf
@@ -68,6 +68,7 @@ class LinearSpec:
         c.dropout_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         c.rows_per_sample = int(rows_per_sample)
         c.gelu_aux_is_grad = 1 if gelu_aux_is_grad else 0
+        c.dy_has_sum = 1 if dy_has_sum else 0
         return c
 
     def n_in_streams(self, x_tasks_given, dropout_p):
@@ -142,16 +143,19 @@ def linear_fwd(spec, x, w_bf16, bias, a_cat, b_cat, *, x_tasks_given=False, act_
 
 
 def linear_bwd_input(spec, dy, wt_bf16, a_cat_t, b_cat_t, *, x_tasks_given=False, gelu_aux=None, aux_is_grad=False,
-                     path_scale=None, rows_per_sample=0, dropout_p=0.0, seed=0, save_g=False):
-    """dy: [S_out, M, N] -> dx [1 (+T), M, K], g_save [M, R] or None."""
+                     dy_has_sum=False, path_scale=None, rows_per_sample=0, dropout_p=0.0, seed=0, save_g=False):
+    """dy: [S_out, M, N] (dy_has_sum: [S_out + 1, M, N], last stream = sum of the others, see scale_rows_sum)
+    -> dx [1 (+T), M, K], g_save [M, R] or None."""
     _chk(dy, BF16, "dy"); _chk(wt_bf16, BF16, "wt_bf16"); _chk(gelu_aux, BF16, "gelu_aux")
     S, M, Nf = dy.shape
+    if dy_has_sum:
+        S -= 1
     if S != spec.S_out or Nf != spec.Nf:
         raise ValueError(f"linear_bwd_input: dy shape {tuple(dy.shape)} does not match the layer ({spec.S_out}, M, {spec.Nf})")
     xt = x_tasks_given and spec.T > 0
     dx = torch.empty((1 + (spec.T if xt else 0), M, spec.K), dtype=BF16, device=dy.device)
     g = torch.empty((M, spec.R_pad), dtype=BF16, device=dy.device) if (save_g and spec.r_shared > 0) else None
-    c = spec.cfg(M, x_tasks_given, dropout_p, seed, rows_per_sample, gelu_aux_is_grad=aux_is_grad)
+    c = spec.cfg(M, x_tasks_given, dropout_p, seed, rows_per_sample, gelu_aux_is_grad=aux_is_grad, dy_has_sum=dy_has_sum)
     N.call("mtl_linear_bwd_input", ctypes.byref(c), N.ptr(dy), N.ptr(wt_bf16), N.ptr(a_cat_t), N.ptr(b_cat_t),
            N.ptr(dx), N.ptr(gelu_aux), N.ptr(path_scale), N.ptr(g), N.stream(),
            meta=("bwd_input", M, spec.K, spec.Nf, dx.shape[0], S, spec.R_pad, sum(spec.ranks), False))
@@ -298,6 +302,15 @@ def scale_rows(x, scale, rows_per_sample):
     S, M, C = x.shape
     y = torch.empty_like(x)
     N.call("mtl_scale_rows", N.ptr(x), N.ptr(scale), N.ptr(y), S, M, C, rows_per_sample, N.stream())
+    return y
+
+
+def scale_rows_sum(x, scale, rows_per_sample):
+    """x [S, M, C] -> y [S + 1, M, C]: y[s] = x[s] * scale[s, sample] (scale None: copy), y[S] = sum_s y[s]."""
+    _chk(x, BF16, "x"); _chk(scale, torch.float32, "scale")
+    S, M, C = x.shape
+    y = torch.empty((S + 1, M, C), dtype=BF16, device=x.device)
+    N.call("mtl_scale_rows_sum", N.ptr(x), N.ptr(scale), N.ptr(y), S, M, C, int(rows_per_sample), N.stream())
     return y
 
 

@@ -223,6 +223,33 @@ def test_linear_gelu_grad_factor(ops):
     check(dx, pre2.grad, what="d pre-activation (factor)")
 
 
+def test_linear_bwd_input_presummed_stream(ops):
+    """cfg.dy_has_sum: the frozen product reads sum_j ps_j dy_j from one extra stream written by mtl_scale_rows_sum;
+    result == the (1+T)-stream form == autograd of the reference layer with DropPath scales."""
+    M, K, N, T = 784, 384, 96, 4
+    spec, p, tasks, tscale = make_layer(ops, "ps", K, N, 64, [4] * T)
+    wb, wt, a_cat, b_cat, a_cat_t, b_cat_t = pack(ops, spec, p, tasks)
+    rps = M // 4
+    dy = bf(dev(detgen.uniform("ps.dy", (1 + T, M, N))))
+    ps = dev(detgen.uniform("ps.ps", (1 + T, 4), 0.0, 2.0))
+    ext = ops.scale_rows_sum(dy, ps, rps)
+    scaled = ops.scale_rows(dy, ps, rps)
+    assert torch.equal(ext[:1 + T], scaled)
+    check(ext[1 + T], scaled.float().sum(0), what="stream sum")
+    dx_a, g_a = ops.linear_bwd_input(spec, ext, wt, a_cat_t, b_cat_t, x_tasks_given=True, dy_has_sum=True, save_g=True)
+    dx_b, g_b = ops.linear_bwd_input(spec, scaled, wt, a_cat_t, b_cat_t, x_tasks_given=True, save_g=True)
+    check(dx_a, dx_b.float(), what="dx presummed vs streams")
+    assert torch.equal(g_a, g_b)
+    xf = bf(dev(detgen.uniform("ps.x", (1 + T, M, K)))).float().requires_grad_()
+    _, _, out = ref_linear(p, tasks, tscale, xf[0], {t: xf[1 + i] for i, t in enumerate(tasks)}, False, None, ps, rps)
+    (out * dy.float()).sum().backward()
+    check(dx_a, xf.grad, what="dx presummed vs autograd")
+    # without scales: plain copy + sum
+    ext2 = ops.scale_rows_sum(dy, None, 0)
+    assert torch.equal(ext2[:1 + T], dy)
+    check(ext2[1 + T], dy.float().sum(0), what="stream sum (no scale)")
+
+
 def test_linear_dropout_stream(ops):
     """LoRA dropout (lora.py:258): adapters of the shared input read D(x), the frozen product reads x."""
     M, K, N, p_drop, seed = 392, 96, 96, 0.25, 1234

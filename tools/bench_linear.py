@@ -65,7 +65,11 @@ def main():
         dy = torch.randn(S_out, M, N, device=dev, generator=g).to(BF)
         n_dx = 1 + (T if xt else 0)
         aux = torch.randn(n_dx, M, K, device=dev, generator=g).to(BF) if kind.startswith("fc2_bwd") else None
-        fn = lambda: ops.linear_bwd_input(spec, dy, wt, a_cat_t, b_cat_t, x_tasks_given=xt, gelu_aux=aux, aux_is_grad=True, dropout_p=p, seed=1, save_g=True)
+        presum = S_out > 1 and K >= 2 * N   # what LinearEngine.backward does for fc2-shaped layers with task streams
+        if presum:
+            dy = ops.scale_rows_sum(dy, None, 0)
+        fn = lambda: ops.linear_bwd_input(spec, dy, wt, a_cat_t, b_cat_t, x_tasks_given=xt, gelu_aux=aux, aux_is_grad=True,
+                                          dy_has_sum=presum, dropout_p=p, seed=1, save_g=True)
         meta = ("bwd_input", M, K, N, n_dx, S_out, spec.R_pad, sum(spec.ranks), False)
     for _ in range(3):
         fn()
