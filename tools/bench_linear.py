@@ -22,6 +22,10 @@ CASES = {
     "qkv_fwd": (401408, 96, 288, 64, [], "qkv"),
     "fc2_bwd": (401408, 384, 96, 64, [4] * 4, "fc2_bwd"),
     "fc1_bwd": (401408, 96, 384, 64, [4] * 4, "fc1_bwd"),
+    "proj_bwd": (401408, 96, 96, 64, [4] * 4, "proj_bwd"),
+    "qkv_bwd": (401408, 96, 288, 64, [], "qkv_bwd"),
+    "s1_fc2_bwd": (100352, 768, 192, 64, [4] * 4, "fc2_bwd"),
+    "s1_fc1_fwd": (100352, 192, 768, 64, [4] * 4, "fc1"),
     "s2_fc1_fwd": (25088, 384, 1536, 64, [], "fc1_single"),
     "s2_fc2_bwd": (25088, 1536, 384, 64, [], "fc2_bwd_single"),
     "s3_fc2_bwd": (6272, 3072, 768, 64, [4] * 4, "fc2_bwd"),
@@ -65,7 +69,8 @@ def main():
         dy = torch.randn(S_out, M, N, device=dev, generator=g).to(BF)
         n_dx = 1 + (T if xt else 0)
         aux = torch.randn(n_dx, M, K, device=dev, generator=g).to(BF) if kind.startswith("fc2_bwd") else None
-        presum = S_out > 1 and K >= 2 * N   # what LinearEngine.backward does for fc2-shaped layers with task streams
+        # what LinearEngine.backward does for fc2-shaped layers with task streams and for DropPath layers (proj)
+        presum = S_out > 1 and (K >= 2 * N or kind == "proj_bwd")
         if presum:
             dy = ops.scale_rows_sum(dy, None, 0)
         fn = lambda: ops.linear_bwd_input(spec, dy, wt, a_cat_t, b_cat_t, x_tasks_given=xt, gelu_aux=aux, aux_is_grad=True,
