@@ -167,8 +167,10 @@ def linear_bwd_params(spec, x, dy, u_save, g_save, *, x_tasks_given=False, x_gel
     """-> (da_cat [R, K], db_cat [N, R]) fp32, packed like a_cat / b_cat."""
     _chk(x, BF16, "x"); _chk(dy, BF16, "dy"); _chk(u_save, BF16, "u_save"); _chk(g_save, BF16, "g_save")
     M = dy.shape[1]
-    da = torch.zeros((spec.R_pad, spec.K), dtype=torch.float32, device=dy.device)
-    db = torch.zeros((spec.Nf, spec.R_pad), dtype=torch.float32, device=dy.device)
+    # one zero-fill for both accumulators
+    buf = torch.zeros(spec.R_pad * (spec.K + spec.Nf), dtype=torch.float32, device=dy.device)
+    da = buf[:spec.R_pad * spec.K].view(spec.R_pad, spec.K)
+    db = buf[spec.R_pad * spec.K:].view(spec.Nf, spec.R_pad)
     c = spec.cfg(M, x_tasks_given, dropout_p, 0, rows_per_sample)
     N.call("mtl_linear_bwd_params", ctypes.byref(c), N.ptr(x), 1 if x_gelu else 0, N.ptr(dy), N.ptr(u_save),
            N.ptr(g_save), N.ptr(path_scale), N.ptr(da), N.ptr(db), N.stream(),
@@ -281,8 +283,11 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, merge_hw=None, want_param
     C = gamma.numel()
     rows = mean.numel()
     dx = torch.empty_like(x)
-    dg = torch.zeros_like(gamma) if want_param_grads else None
-    db = torch.zeros_like(gamma) if want_param_grads else None
+    if want_param_grads:
+        gb = torch.zeros((2, C), dtype=gamma.dtype, device=gamma.device)   # one zero-fill for both accumulators
+        dg, db = gb[0], gb[1]
+    else:
+        dg = db = None
     H, W = (0, 0) if merge_hw is None else merge_hw
     N.call("mtl_layernorm_bwd", N.ptr(dy), N.ptr(x), N.ptr(gamma), N.ptr(mean), N.ptr(rstd), N.ptr(dres), N.ptr(dx),
            N.ptr(dg), N.ptr(db), rows, C, 0 if merge_hw is None else 1, H, W, N.stream())
