@@ -492,10 +492,13 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               uint32_t db = 0;
               if (multi) {
                 const uint32_t k = G / kGroups;
-                if (p.d_shared) {   // one delta accumulator serves both groups (item G is its G-th use)
-                  db = 0;
+                if (p.d_shared) {
+                  // One delta accumulator serves both groups (item G is its G-th use). This thread sees every phase
+                  // of d_empty(0) in order; the groups alternate, so each gets its OWN full barrier (a group waiting on a
+                  // shared one would skip every other phase and mistake an old completion for its own).
                   mbar_wait(d_empty(0), (G & 1u) ^ 1u, p.wait_hint_ns);
                   tc_fence_after();
+                  db = (G % kGroups) * 2;
                   acc = tmem_base + d_col0;
                 } else {
                   db = (G % kGroups) * 2 + k % p.n_dbuf;
@@ -621,8 +624,9 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         bool p_waited = false;
         for (int j = 0; j < n_items; ++j, ++G) {
           if ((G % kGroups) != grp) continue;
-          const uint32_t kk = G / kGroups, dbuf = kk & dsh, db = p.d_shared ? 0u : grp * 2 + dbuf;
-          const uint32_t d_parity = p.d_shared ? (G & 1u) : ((kk >> dsh) & 1u);
+          // d_shared: full barrier of this group (grp * 2), its kk-th use; the empty barrier is the shared d_empty(0)
+          const uint32_t kk = G / kGroups, dbuf = kk & dsh, db = p.d_shared ? grp * 2 : grp * 2 + dbuf;
+          const uint32_t d_parity = p.d_shared ? (kk & 1u) : ((kk >> dsh) & 1u);
           // Epilogue inputs that do not depend on the accumulators (the GELU' argument of the fc2 backward, the residual
           // of proj / fc2 forward) are staged by TMA into the very slab the half's output will be written to, one
           // 64-column half ahead (across item and tile boundaries), so their HBM latency never stalls the math.
@@ -838,7 +842,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             }
           }
           tc_fence_before();
-          mbar_arrive(d_empty(db));
+          mbar_arrive(d_empty(p.d_shared ? 0u : db));
           tr.ev(7000000ull + ci * 10 + j);   // item done
         }
         if (multi) {

@@ -282,6 +282,31 @@ def test_linear_dropout_stream(ops):
     check(db[:, 16:20], pr["lora_tasks_B.t0"].grad, tol=2e-2, what="dB task0")
 
 
+@pytest.mark.parametrize("r_s", [4, 64])
+def test_linear_bwd_input_dropout_long_contraction(ops, r_s):
+    """Single-stream input gradient with LoRA dropout and a long contraction (stage-2/3 layers): dense accumulator
+    double-buffered + ONE delta accumulator shared by the two epilogue groups, 128-column chunks, several work items
+    per persistent CTA. The adapter part is made as large as the frozen part so that a mix-up of chunks shows."""
+    M, K, N, p_drop, seed = 40000, 384, 1536, 0.25, 77
+    spec = ops.LinearSpec(K, N, r_s, [], 4.0, [])
+    W = dev(detgen.uniform(f"dl.w{r_s}", (N, K), -0.02, 0.02))
+    A = dev(detgen.uniform(f"dl.a{r_s}", (r_s, K), -0.2, 0.2))
+    B = dev(detgen.uniform(f"dl.b{r_s}", (N, r_s), -0.1, 0.1)) * (8.0 / r_s) ** 0.5
+    wb, wt = ops.cast_transpose(W)
+    a_cat, b_cat, a_cat_t, b_cat_t = ops.pack_adapters(spec, A, B, [], [])
+    dy = bf(dev(detgen.uniform(f"dl.dy{r_s}", (1, M, N))))
+    dx, g = ops.linear_bwd_input(spec, dy, wt, a_cat_t, b_cat_t, dropout_p=p_drop, seed=seed, save_g=True)
+    mask = (ops.dropout(torch.ones((M, K), dtype=torch.bfloat16, device="cuda"), p_drop, seed) != 0).float() / (1 - p_drop)
+    dyf = dy[0].float()
+    dense = dyf @ bf(W).float()
+    G = 4.0 * (dyf @ bf(B).float())
+    delta = mask * (bf(G).float() @ bf(A).float())
+    assert delta.abs().max() > 0.3 * dense.abs().max()      # the adapter part matters in this test
+    check(g[:, :r_s], G, what="G")
+    check(dx[0], dense + delta, what="dx (dense + masked adapter part)")
+    check(dx[0].float() - dense, delta, tol=3e-2, what="adapter part of dx")
+
+
 def test_xty(ops):
     M, a, b = 5000, 192, 384
     P = bf(dev(detgen.uniform("xty.p", (M, a))))
