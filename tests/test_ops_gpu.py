@@ -208,6 +208,15 @@ def test_linear_gelu_grad_factor(ops):
     pdf = 0.3989422804014327 * torch.exp(-0.5 * pre * pre)
     check(yg, cdf + pre * pdf, what="GELU' factor")
     check(y_act, act, what="gelu")
+    # with LoRA dropout: input stream D(x[0]) appended, and the dropped copy of GELU(y[0]) (seed + 1) comes out last
+    p_drop, seed = 0.25, 99
+    xd = torch.cat([x, ops.dropout(x[:1], p_drop, seed)]).contiguous()
+    yg2, y_act2, _ = ops.linear_fwd(spec, xd, wb, p.get("linear.bias"), a_cat, b_cat, x_tasks_given=True, act_gelu=True,
+                                    gelu_grad=True, dropout_p=p_drop, seed=seed)
+    assert y_act2.shape[0] == 4
+    assert torch.equal(y_act2[3], ops.dropout(y_act2[:1].contiguous(), p_drop, seed + 1)[0])
+    check(y_act2[1:3], act[1:3], what="gelu of the task streams (their adapters read x_t, not D(x))")
+    check(yg2[1:3], (cdf + pre * pdf)[1:3], what="GELU' factor of the task streams")
     # consuming layer (fc2): dx = (dy W + ...) * factor
     spec2, p2, tasks2, tscale2 = make_layer(ops, "gg2", N, K, 64, [4, 4])
     wb2, wt2, a2, b2, a2t, b2t = pack(ops, spec2, p2, tasks2)
@@ -305,6 +314,40 @@ def test_linear_bwd_input_dropout_long_contraction(ops, r_s):
     check(g[:, :r_s], G, what="G")
     check(dx[0], dense + delta, what="dx (dense + masked adapter part)")
     check(dx[0].float() - dense, delta, tol=3e-2, what="adapter part of dx")
+
+
+@pytest.mark.parametrize("K,N", [(384, 96), (1536, 384)])
+def test_linear_bwd_input_last_block_fc2(ops, K, N):
+    """The fc2 input gradient of a stage's last block exactly as LinearEngine.backward issues it: 1+T gradient streams
+    plus their pre-summed stream (cfg.dy_has_sum), LoRA dropout on the shared adapter's input (mask on dx[0]'s adapter
+    part), task inputs given (dx[t] = G_t A_t), GELU' factor multiplied in the epilogue (cfg.gelu_aux_is_grad).
+    (384, 96): 64-column chunks, two dense buffers; (1536, 384): long contraction, 128-column chunks, one dense buffer."""
+    M, T, p_drop, seed = 20000, 4, 0.25, 4321
+    spec = ops.LinearSpec(K, N, 64, [4] * T, 4.0, [4.0] * T)
+    W = dev(detgen.uniform(f"lb.w{K}", (N, K), -0.03, 0.03))
+    As = dev(detgen.uniform(f"lb.as{K}", (64, K), -0.1, 0.1))
+    Bs = dev(detgen.uniform(f"lb.bs{K}", (N, 64), -0.05, 0.05))
+    At = [dev(detgen.uniform(f"lb.at{K}.{t}", (4, K), -0.2, 0.2)) for t in range(T)]
+    Bt = [dev(detgen.uniform(f"lb.bt{K}.{t}", (N, 4), -0.2, 0.2)) for t in range(T)]
+    wb, wt = ops.cast_transpose(W)
+    a_cat, b_cat, a_cat_t, b_cat_t = ops.pack_adapters(spec, As, Bs, At, Bt)
+    dy = bf(dev(detgen.uniform(f"lb.dy{K}", (1 + T, M, N))))
+    fac = bf(dev(detgen.uniform(f"lb.f{K}", (1 + T, M, K), -0.2, 1.1)))
+    ext = ops.scale_rows_sum(dy, None, 0)
+    dx, g = ops.linear_bwd_input(spec, ext, wt, a_cat_t, b_cat_t, x_tasks_given=True, gelu_aux=fac, aux_is_grad=True,
+                                 dy_has_sum=True, dropout_p=p_drop, seed=seed, save_g=True)
+    mask = (ops.dropout(torch.ones((M, K), dtype=torch.bfloat16, device="cuda"), p_drop, seed) != 0).float() / (1 - p_drop)
+    dyf = dy.float()
+    dense = ext[1 + T].float() @ bf(W).float()
+    Gs = bf(4.0 * (dyf[0] @ bf(Bs).float())).float()
+    ref0 = (dense + mask * (Gs @ bf(As).float())) * fac[0].float()
+    check(dx[0], ref0, what="dx[0]")
+    check(dx[0].float() - dense * fac[0].float(), mask * (Gs @ bf(As).float()) * fac[0].float(), tol=3e-2,
+          what="adapter part of dx[0]")
+    for t in range(T):
+        Gt = bf(4.0 * (dyf[1 + t] @ bf(Bt[t]).float())).float()
+        check(dx[1 + t], (Gt @ bf(At[t]).float()) * fac[1 + t].float(), what=f"dx[{1 + t}]")
+        check(g[:, 64 + 16 * t:64 + 16 * t + 4], Gt, what=f"G task {t}")
 
 
 def test_xty(ops):
