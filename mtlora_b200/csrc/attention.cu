@@ -22,6 +22,24 @@ constexpr int NP = 64;        // padded tokens per window
 constexpr int QS = 40;        // smem row stride (bf16) for [NP][HD] tiles: 80 B, conflict-free ldmatrix
 constexpr int PS = 72;        // smem row stride (bf16) for [NP][NP] tiles
 
+// single-instruction MUFU forms (arguments are max-subtracted / positive sums: no range handling needed;
+// ex2.approx(-inf) = 0, relative error 2^-22)
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct WinGeom {
   int H, W, ws, shift, nwh, nww, N;
 };
@@ -205,7 +223,7 @@ __global__ void __launch_bounds__(128, 4) win_attn_fwd_kernel(const AttnParams p
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float m = (e < 2) ? mx0 : mx1;
-        const float pv = exp2f(s[nt][e] - m);
+        const float pv = fast_ex2(s[nt][e] - m);
         s[nt][e] = pv;
         if (e < 2) sum0 += pv; else sum1 += pv;
       }
@@ -214,11 +232,11 @@ __global__ void __launch_bounds__(128, 4) win_attn_fwd_kernel(const AttnParams p
     sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
     sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
     sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-    const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+    const float inv0 = fast_rcp(sum0), inv1 = fast_rcp(sum1);
     if (p.lse != nullptr && t4 == 0) {
       float* l = p.lse + (static_cast<size_t>(win) * p.nH + head) * NP;
-      l[i0] = (mx0 + log2f(sum0)) * 0.6931471805599453f;   // natural-log units
-      l[i1] = (mx1 + log2f(sum1)) * 0.6931471805599453f;
+      l[i0] = (mx0 + fast_lg2(sum0)) * 0.6931471805599453f;   // natural-log units
+      l[i1] = (mx1 + fast_lg2(sum1)) * 0.6931471805599453f;
     }
 
     // O = P V  (P from registers, V via transposed ldmatrix)
@@ -404,10 +422,10 @@ __global__ void __launch_bounds__(128, 3) win_attn_bwd_kernel(const AttnBwdParam
     }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = exp2f(s[nt][0] - lse0);
-      s[nt][1] = exp2f(s[nt][1] - lse0);
-      s[nt][2] = exp2f(s[nt][2] - lse1);
-      s[nt][3] = exp2f(s[nt][3] - lse1);
+      s[nt][0] = fast_ex2(s[nt][0] - lse0);
+      s[nt][1] = fast_ex2(s[nt][1] - lse0);
+      s[nt][2] = fast_ex2(s[nt][2] - lse1);
+      s[nt][3] = fast_ex2(s[nt][3] - lse1);
     }
     // ---- dP = dO V^T -------------------------------------------------------------------------
     float dp[8][4];

@@ -353,12 +353,12 @@ int launch_xty_groups(const XtyOperand* wide, const XtyOperand* rank, const XtyJ
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  // row splits: enough units to fill and balance the persistent grid; a unit costs its rows plus ~2 steps of
-  // pipeline fill / reduction epilogue
+  // row splits: enough units to fill and balance the persistent grid; a unit costs its rows plus ~6 steps' worth of
+  // pipeline fill, accumulator drain and red.global epilogue (measured ~3 us), so small problems take ONE unit per CTA
   const long max_splits = (M + 4 * XG_ROWS - 1) / (4 * XG_ROWS);
   long best_splits = 1;
   double best_cost = 1e300;
-  const long lo = (2L * n_sm + jobs - 1) / jobs, hi = (8L * n_sm + jobs - 1) / jobs;
+  const long lo = (1L * n_sm + jobs - 1) / jobs, hi = (8L * n_sm + jobs - 1) / jobs;
   for (long sp = (lo < 1 ? 1 : lo); sp <= (hi < 1 ? 1 : hi); ++sp) {
     const long s = sp > max_splits ? max_splits : sp;
     long mc = (M + s - 1) / s;
@@ -366,7 +366,7 @@ int launch_xty_groups(const XtyOperand* wide, const XtyOperand* rank, const XtyJ
     const long ns = (M + mc - 1) / mc;
     const long units = ns * jobs;
     const long waves = (units + n_sm - 1) / n_sm;
-    const double cost = static_cast<double>(waves) * (mc + 2.0 * XG_ROWS);
+    const double cost = static_cast<double>(waves) * (mc + 6.0 * XG_ROWS);
     if (cost < best_cost * 0.999) {
       best_cost = cost;
       best_splits = ns;
