@@ -176,6 +176,15 @@ int mtl_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
                       const void* dres, void* dx, float* dgamma, float* dbeta, int64_t rows, int32_t C,
                       int32_t merge, int32_t H, int32_t W, mtl_stream_t stream);
 
+/* PatchEmbed.forward (swin_transformer_mtlora.py:597-605) for patch_size 4, in_chans 3, embed_dim 96 / 128:
+ * y = LayerNorm(Conv2d(3, E, k=4, s=4)(x).flatten(2).transpose(1, 2)) in one pass over the fp32 NCHW image.
+ * x: [B, 3, H, W] fp32; w: [E, 3, 4, 4] fp32; bias, gamma, beta: [E] fp32 (gamma NULL: no norm).
+ * y: [B*H/4*W/4, E] bf16. Optional outputs for backward: proj (the projection + bias, bf16, input of
+ * mtl_layernorm_bwd), patches (im2col rows [B*L, 48] bf16, operand of dW = d_proj^T patches via mtl_xty), mean, rstd. */
+int mtl_patch_embed_fwd(const float* x, const float* w, const float* bias, const float* gamma, const float* beta,
+                        void* proj, void* y, void* patches, float* mean, float* rstd, int32_t B, int32_t H, int32_t W,
+                        int32_t E, float eps, mtl_stream_t stream);
+
 /* Elementwise helpers of the block */
 int mtl_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, mtl_stream_t stream);
 int mtl_scale_rows(const void* x, const float* scale, void* y, int32_t S, int64_t M, int32_t C,

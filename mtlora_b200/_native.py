@@ -76,6 +76,7 @@ SIGNATURES = {
     "mtl_dropout": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_uint64, c_void_p]),
     "mtl_scale_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int32, c_void_p]),
     "mtl_add": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "mtl_patch_embed_fwd": (c_int, [c_void_p] * 10 + [c_int32] * 4 + [c_float, c_void_p]),
     "mtl_scale_rows_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int32, c_void_p]),
     "mtl_sum_streams": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p]),
 }

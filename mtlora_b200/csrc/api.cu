@@ -477,6 +477,11 @@ int mtl_scale_rows(const void* x, const float* scale, void* y, int32_t Sn, int64
   MTL_REQUIRE(x != nullptr && y != nullptr && scale != nullptr, "scale_rows: NULL argument");
   return launch_scale_rows(x, scale, y, Sn, M, C, rows_per_sample, S(stream));
 }
+int mtl_patch_embed_fwd(const float* x, const float* w, const float* bias, const float* gamma, const float* beta,
+                        void* proj, void* y, void* patches, float* mean, float* rstd, int32_t B, int32_t H, int32_t W,
+                        int32_t E, float eps, mtl_stream_t stream) {
+  return launch_patch_embed_fwd(x, w, bias, gamma, beta, proj, y, patches, mean, rstd, B, H, W, E, eps, S(stream));
+}
 int mtl_scale_rows_sum(const void* x, const float* scale, void* y, int32_t Sn, int64_t M, int32_t C,
                        int32_t rows_per_sample, mtl_stream_t stream) {
   MTL_REQUIRE(x != nullptr && y != nullptr, "scale_rows_sum: NULL argument");

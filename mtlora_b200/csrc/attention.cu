@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(128, 4) win_attn_fwd_kernel(const AttnParams p
   __shared__ __align__(16) __nv_bfloat16 Ks[NP * QS];
   __shared__ __align__(16) __nv_bfloat16 Vs[NP * QS];
   __shared__ float bias_s[225];
+  __shared__ int2 tok_yx[NP];   // (row, column) of every window token: one division per token per CTA, not per pair
   __shared__ __align__(8) int reg_s[NP];
 
   const int head = blockIdx.y;
@@ -110,6 +111,10 @@ __global__ void __launch_bounds__(128, 4) win_attn_fwd_kernel(const AttnParams p
   const int n_win = p.B * nW;
   const int tbl = (2 * g.ws - 1) * (2 * g.ws - 1);
   for (int i = threadIdx.x; i < tbl; i += blockDim.x) bias_s[i] = p.rpb[i * p.nH + head];
+  if (threadIdx.x < NP) {
+    const int ty = threadIdx.x / g.ws;
+    tok_yx[threadIdx.x] = make_int2(ty, threadIdx.x - ty * g.ws);
+  }
   if (threadIdx.x < NP) reg_s[threadIdx.x] = 0;
   const int C3 = 3 * p.C;
   __syncthreads();
@@ -128,7 +133,7 @@ __global__ void __launch_bounds__(128, 4) win_attn_fwd_kernel(const AttnParams p
       float b = -INFINITY;
       if (j < g.N) {
         const int ic = i < g.N ? i : 0;
-        const int iy = ic / g.ws, ix = ic - iy * g.ws, jy = j / g.ws, jx = j - jy * g.ws;
+        const int iy = tok_yx[ic].x, ix = tok_yx[ic].y, jy = tok_yx[j].x, jx = tok_yx[j].y;
         b = bias_s[(iy - jy + g.ws - 1) * (2 * g.ws - 1) + (ix - jx + g.ws - 1)] * kLog2e;
       }
       bias_r[nt][e] = b;
@@ -308,6 +313,7 @@ __global__ void __launch_bounds__(128, 3) win_attn_bwd_kernel(const AttnBwdParam
   __shared__ __align__(16) __nv_bfloat16 Ps[NP * PS];
   __shared__ __align__(16) __nv_bfloat16 dSs[NP * PS];
   __shared__ float bias_s[225];
+  __shared__ int2 tok_yx[NP];   // (row, column) of every window token: one division per token per CTA, not per pair
   __shared__ float dbias_s[225];
   __shared__ __align__(8) int reg_s[NP];
 
@@ -321,6 +327,10 @@ __global__ void __launch_bounds__(128, 3) win_attn_bwd_kernel(const AttnBwdParam
   for (int i = threadIdx.x; i < tbl; i += blockDim.x) {
     bias_s[i] = p.rpb[i * p.nH + head];
     dbias_s[i] = 0.f;
+  }
+  if (threadIdx.x < NP) {
+    const int ty = threadIdx.x / g.ws;
+    tok_yx[threadIdx.x] = make_int2(ty, threadIdx.x - ty * g.ws);
   }
   const int C3 = 3 * p.C;
   float dsacc[8][4];  // sum over this CTA's windows of dS (for d relative_position_bias_table)
@@ -340,7 +350,7 @@ __global__ void __launch_bounds__(128, 3) win_attn_bwd_kernel(const AttnBwdParam
       float b = -INFINITY;
       if (j < g.N) {
         const int ic = i < g.N ? i : 0;
-        const int iy = ic / g.ws, ix = ic - iy * g.ws, jy = j / g.ws, jx = j - jy * g.ws;
+        const int iy = tok_yx[ic].x, ix = tok_yx[ic].y, jy = tok_yx[j].x, jx = tok_yx[j].y;
         b = bias_s[(iy - jy + g.ws - 1) * (2 * g.ws - 1) + (ix - jx + g.ws - 1)] * kLog2e;
       }
       bias_r[nt][e] = b;
@@ -540,7 +550,7 @@ __global__ void __launch_bounds__(128, 3) win_attn_bwd_kernel(const AttnBwdParam
         const int i = (e < 2) ? i0 : i1;
         const int j = nt * 8 + t4 * 2 + (e & 1);
         if (i < g.N && j < g.N) {
-          const int iy = i / g.ws, ix = i - iy * g.ws, jy = j / g.ws, jx = j - jy * g.ws;
+          const int iy = tok_yx[i].x, ix = tok_yx[i].y, jy = tok_yx[j].x, jx = tok_yx[j].y;
           atomicAdd(&dbias_s[(iy - jy + g.ws - 1) * (2 * g.ws - 1) + (ix - jx + g.ws - 1)], dsacc[nt][e]);
         }
       }

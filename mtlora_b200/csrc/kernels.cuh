@@ -48,6 +48,13 @@ int launch_pack_adapters(const float* const* a_ptrs, const float* const* b_ptrs,
 // fp32 [rows, cols] -> bf16 copy and/or bf16 transposed copy
 int launch_cast_transpose(const float* w, void* w_bf16, void* wt_bf16, int rows, int cols, cudaStream_t stream);
 
+// patch_embed.cu ----------------------------------------------------------------------------------
+// tokens = LayerNorm(Conv2d(k4, s4)(x) + bias): x fp32 [B, 3, H, W] -> proj (pre-norm, bf16), y (bf16), patches (im2col,
+// bf16 [B*L, 48]), mean / rstd; proj / patches / mean / rstd / gamma may be null.
+int launch_patch_embed_fwd(const float* x, const float* w, const float* bias, const float* gamma, const float* beta,
+                           void* proj, void* y, void* patches, float* mean, float* rstd, int B, int H, int W, int E,
+                           float eps, cudaStream_t stream);
+
 // xty.cu ------------------------------------------------------------------------------------------
 // C[a, b] += sum_m rowscale(m) * P[m, a] * Q[m, b]   (fp32 atomics; P, Q bf16 row-major with leading dims)
 // q_gelu != 0 applies exact GELU to Q elements on load (recomputing the fc2 input from the saved fc1 output).

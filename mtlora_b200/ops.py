@@ -294,6 +294,26 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, merge_hw=None, want_param
     return dx, dg, db
 
 
+def patch_embed_fwd(x, w, bias, gamma, beta, eps=1e-5, save=True):
+    """x [B, 3, H, W] fp32 -> y [B, L, E] bf16 (+ proj, patches, mean, rstd when save) — Conv2d(k4, s4) + bias + LayerNorm."""
+    _chk(x, torch.float32, "x"); _chk(w, torch.float32, "weight"); _chk(bias, torch.float32, "bias")
+    _chk(gamma, torch.float32, "gamma"); _chk(beta, torch.float32, "beta")
+    B, C, H, W = x.shape
+    E = w.shape[0]
+    if C != 3 or tuple(w.shape[1:]) != (3, 4, 4):
+        raise ValueError("patch_embed_fwd: only in_chans=3, patch_size=4 are supported")
+    L = (H // 4) * (W // 4)
+    dev = x.device
+    y = torch.empty((B, L, E), dtype=BF16, device=dev)
+    proj = torch.empty((B * L, E), dtype=BF16, device=dev) if save else None
+    patches = torch.empty((B * L, 48), dtype=BF16, device=dev) if save else None
+    mean = torch.empty((B * L,), dtype=torch.float32, device=dev) if save else None
+    rstd = torch.empty((B * L,), dtype=torch.float32, device=dev) if save else None
+    N.call("mtl_patch_embed_fwd", N.ptr(x), N.ptr(w), N.ptr(bias), N.ptr(gamma), N.ptr(beta), N.ptr(proj), N.ptr(y),
+           N.ptr(patches), N.ptr(mean), N.ptr(rstd), B, H, W, E, float(eps), N.stream())
+    return y, proj, patches, mean, rstd
+
+
 def dropout(x, p, seed):
     _chk(x, BF16, "x")
     y = torch.empty_like(x)

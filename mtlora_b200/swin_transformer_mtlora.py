@@ -113,6 +113,12 @@ def _require_cuda(x, what):
                            "(build libmtlora_b200.so and run on the B200)")
 
 
+def _autocast_cuda_dtype():
+    if hasattr(torch, "get_autocast_dtype"):
+        return torch.get_autocast_dtype("cuda")
+    return torch.get_autocast_gpu_dtype()
+
+
 def _out_dtype(x):
     """dtype handed back to the caller: the input dtype, or bf16 under autocast (what the reference's linears would
     produce under `torch.autocast(dtype=bfloat16)`, main.py:341)."""
@@ -831,12 +837,41 @@ class _LayerNormFn(torch.autograd.Function):
         return dx.view(dy.shape), dw, db, None
 
 
+class _PatchEmbedFn(torch.autograd.Function):
+    """Conv2d(3, E, k4, s4) + bias + LayerNorm in one kernel (mtl_patch_embed_fwd); backward = mtl_layernorm_bwd on the
+    saved projection, dW = d_proj^T patches and db = column sums of d_proj through mtl_xty. The image gets no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, gamma, beta, eps):
+        need = any(ctx.needs_input_grad[1:])
+        y, proj, patches, mean, rstd = ops.patch_embed_fwd(x.contiguous(), w.detach().float().contiguous(),
+                                                           b.detach().float(), gamma.detach().float(),
+                                                           beta.detach().float(), eps, save=need)
+        if need:
+            ctx.save_for_backward(proj, patches, mean, rstd, gamma.detach().float())
+            ctx.wshape = w.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        proj, patches, mean, rstd, gamma = ctx.saved_tensors
+        E = proj.shape[1]
+        dy2 = dy.reshape(-1, E)
+        if dy2.dtype != BF16 or not dy2.is_contiguous():
+            dy2 = dy2.to(BF16).contiguous()
+        dproj, dgam, dbet = ops.layernorm_bwd(dy2, proj, gamma, mean, rstd)
+        dw = ops.xty(dproj, patches).view(ctx.wshape)                      # [E, 48] = d_proj^T patches
+        ones = torch.ones((dproj.shape[0], 8), dtype=BF16, device=dproj.device)
+        db = ops.xty(dproj, ones)[:, 0].contiguous()
+        return None, dw, db, dgam, dbet, None
+
+
 class PatchEmbed(nn.Module):
     r"""Image to Patch Embedding (reference :568-611: Conv2d k4 s4 + LayerNorm; the convolution stays PyTorch / cuDNN).
 
-    Under bf16 autocast on CUDA the convolution runs channels-last, so its output already is the (B, L, C) token
-    matrix, and the LayerNorm goes through mtl_layernorm_fwd / _bwd in bf16 (one HBM pass) instead of autocast's fp32
-    LayerNorm over a strided view."""
+    Under bf16 autocast on CUDA the standard geometry (patch 4, 3 input channels, embed_dim 96 / 128) runs as ONE
+    kernel (mtl_patch_embed_fwd: projection + bias + LayerNorm, bf16 tokens); other geometries run the convolution
+    channels-last, so its output already is the (B, L, C) token matrix, with the LayerNorm through mtl_layernorm."""
 
     def __init__(self, img_size=224, patch_size=4, in_chans=3, embed_dim=96, norm_layer=None):
         super().__init__()
@@ -856,8 +891,13 @@ class PatchEmbed(nn.Module):
         B, C, H, W = x.shape
         assert H == self.img_size[0] and W == self.img_size[1], \
             f"Input image size ({H}*{W}) doesn't match model ({self.img_size[0]}*{self.img_size[1]})."
-        if (x.is_cuda and type(self.norm) is nn.LayerNorm and torch.is_autocast_enabled()
-                and torch.get_autocast_gpu_dtype() == BF16):
+        bf16_autocast = x.is_cuda and torch.is_autocast_enabled() and _autocast_cuda_dtype() == BF16
+        if (bf16_autocast and type(self.norm) is nn.LayerNorm and x.dtype == torch.float32 and C == 3
+                and tuple(self.patch_size) == (4, 4) and self.embed_dim in (96, 128) and self.proj.bias is not None):
+            # one kernel: patch projection + bias + LayerNorm, bf16 tokens out
+            return _PatchEmbedFn.apply(x, self.proj.weight, self.proj.bias, self.norm.weight, self.norm.bias,
+                                       self.norm.eps)
+        if bf16_autocast and type(self.norm) is nn.LayerNorm:
             y = self.proj(x.contiguous(memory_format=torch.channels_last))   # (B, C, Ph, Pw) bf16, NHWC strides
             y = y.permute(0, 2, 3, 1).contiguous()                           # no copy when the conv answered NHWC
             y = y.view(B, -1, self.embed_dim)

@@ -295,21 +295,23 @@ def test_mark_only_lora_and_state_dict(S):
     assert list(new) == ["layers.0.blocks.0.attn.qkv.linear.weight"]
 
 
-def test_patch_embed_autocast_path(S):
+@pytest.mark.parametrize("E,in_chans", [(96, 3), (128, 3), (96, 4)])
+def test_patch_embed_autocast_path(S, E, in_chans):
     """PatchEmbed under bf16 autocast (channels-last conv + mtl_layernorm) vs Conv2d + LayerNorm evaluated in fp32
     (reference swin_transformer_mtlora.py:597-605), forward and the gradients of every trainable parameter."""
-    pe = S.PatchEmbed(img_size=56, patch_size=4, in_chans=3, embed_dim=96, norm_layer=torch.nn.LayerNorm).cuda()
+    # (96 | 128, 3): the fused mtl_patch_embed_fwd kernel; in_chans 4: channels-last convolution + mtl_layernorm
+    pe = S.PatchEmbed(img_size=56, patch_size=4, in_chans=in_chans, embed_dim=E, norm_layer=torch.nn.LayerNorm).cuda()
     load_det(pe, "pe.")
-    x = detgen.uniform("pe.x", (2, 3, 56, 56), -2.0, 2.0).cuda()
-    gy = detgen.uniform("pe.gy", (2, 196, 96)).cuda()
+    x = detgen.uniform("pe.x", (3, in_chans, 56, 56), -2.0, 2.0).cuda()
+    gy = detgen.uniform("pe.gy", (3, 196, E)).cuda()
     with torch.autocast("cuda", dtype=torch.bfloat16):
         y = pe(x)
-    assert y.dtype == torch.bfloat16 and y.shape == (2, 196, 96)
+    assert y.dtype == torch.bfloat16 and y.shape == (3, 196, E)
     (y.float() * gy).sum().backward()
     got = {n: prm.grad.clone() for n, prm in pe.named_parameters()}
     for prm in pe.parameters():
         prm.grad = None
-    ref = torch.nn.functional.layer_norm(pe.proj(x).flatten(2).transpose(1, 2), (96,), pe.norm.weight, pe.norm.bias, 1e-5)
+    ref = torch.nn.functional.layer_norm(pe.proj(x).flatten(2).transpose(1, 2), (E,), pe.norm.weight, pe.norm.bias, 1e-5)
     (ref * gy).sum().backward()
     close(y, ref, TOL, "patch_embed y")
     for n, prm in pe.named_parameters():
