@@ -26,6 +26,8 @@ CASES = {
     "qkv_bwd": (401408, 96, 288, 64, [], "qkv_bwd"),
     "s1_fc2_bwd": (100352, 768, 192, 64, [4] * 4, "fc2_bwd"),
     "s1_fc1_fwd": (100352, 192, 768, 64, [4] * 4, "fc1"),
+    "s0_fc2_bwd": (401408, 384, 96, 64, [], "fc2_bwd_single"),
+    "s0_proj_bwd": (401408, 96, 96, 64, [], "proj_bwd_single"),
     "s2_fc1_fwd": (25088, 384, 1536, 64, [], "fc1_single"),
     "s2_fc2_bwd": (25088, 1536, 384, 64, [], "fc2_bwd_single"),
     "s3_fc2_bwd": (6272, 3072, 768, 64, [4] * 4, "fc2_bwd"),
