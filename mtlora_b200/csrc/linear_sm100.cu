@@ -964,6 +964,8 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
       bn = 128;
       p.n_pbuf = 1;
     }
+    // (measured: the GELU pair is slower with 128-column items even with three slabs — its long items need the
+    // double-buffered accumulators more than the wider chunks)
     if (cols(bn, p.n_pbuf, 1) > 512) p.n_pbuf = 1;
     if (cols(bn, p.n_pbuf, 2) <= 512) p.n_dbuf = 2;
     // single output stream with separate dense / adapter accumulators (input gradient with LoRA dropout) and a long
