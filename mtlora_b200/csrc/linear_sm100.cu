@@ -128,8 +128,9 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
 // GELU(x) = x * Phi(x), GELU'(x) = Phi(x) + x * phi(x). Two elements per instruction.
 // Evaluated breadth-first over the 8 element pairs of a 16-column granule so that every Horner step issues 8
 // independent FFMA2 (the epilogue runs with only two warps per scheduler: dependent chains would stall the issue port).
-__device__ __forceinline__ void phi16(const float (&v)[16], uint64_t (&phi)[8]) {
-  uint64_t xc[8], t[8], q[8];
+// xc / t (optional outputs): the clamped arguments and their squares, reused by the derivative epilogue
+__device__ __forceinline__ void phi16(const float (&v)[16], uint64_t (&phi)[8], uint64_t (&xc)[8], uint64_t (&t)[8]) {
+  uint64_t q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
     xc[i] = pack2(fminf(fmaxf(v[2 * i], -4.25f), 4.25f), fminf(fmaxf(v[2 * i + 1], -4.25f), 4.25f));
@@ -150,6 +151,10 @@ __device__ __forceinline__ void phi16(const float (&v)[16], uint64_t (&phi)[8]) 
 #pragma unroll
   for (int i = 0; i < 8; ++i) phi[i] = fma2(xc[i], q[i], MTL_C2(0.5f));
 }
+__device__ __forceinline__ void phi16(const float (&v)[16], uint64_t (&phi)[8]) {
+  uint64_t xc[8], t[8];
+  phi16(v, phi, xc, t);
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -169,18 +174,19 @@ __device__ __forceinline__ void gelu16_pack(const float (&v)[16], uint32_t (&pk)
 // GELU(v) and GELU'(v) = Phi(v) + v * pdf(v) for a granule, both packed to bf16x2 (fc1 forward when the consuming
 // fc2 backward wants the derivative factor instead of the pre-activation)
 __device__ __forceinline__ void gelu_and_grad16_pack(const float (&v)[16], uint32_t (&pk_gelu)[8], uint32_t (&pk_grad)[8]) {
-  uint64_t phi[8];
-  phi16(v, phi);
+  uint64_t phi[8], xc[8], t[8];
+  phi16(v, phi, xc, t);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    float g0, g1, d0, d1;
+    float g0, g1, d0, d1, e0, e1;
     const uint64_t v2 = pack2(v[2 * i], v[2 * i + 1]);
     unpack2(mul2(v2, phi[i]), g0, g1);
     pk_gelu[i] = pack_bf16x2(g0, g1);
-    // pdf = exp(-x^2 / 2) / sqrt(2 pi); for |x| > 4 both x * pdf and the clamping error of Phi are < 6e-4
-    const float p0 = 0.39894228040143267794f * ex2_approx(-0.72134752044448170368f * v[2 * i] * v[2 * i]);
-    const float p1 = 0.39894228040143267794f * ex2_approx(-0.72134752044448170368f * v[2 * i + 1] * v[2 * i + 1]);
-    unpack2(fma2(v2, pack2(p0, p1), phi[i]), d0, d1);
+    // x pdf(x) = x exp(-x^2 / 2) / sqrt(2 pi) on the clamped argument (its square comes from the Phi polynomial): beyond
+    // |x| = 4.25 the true value and the clamped one (2e-4) both vanish against GELU' ~ 0 / 1 at bf16 resolution
+    unpack2(mul2(t[i], MTL_C2(-0.72134752044448170368f)), e0, e1);
+    const uint64_t pdf = pack2(ex2_approx(e0), ex2_approx(e1));
+    unpack2(fma2(mul2(xc[i], MTL_C2(0.39894228040143267794f)), pdf, phi[i]), d0, d1);
     pk_grad[i] = pack_bf16x2(d0, d1);
   }
 }
