@@ -32,6 +32,8 @@ enum { MTL_MODE_MATRIX = 0 }; /* MTLoRALinear shared_mode 'matrix' (models/lora.
 enum { MTL_ACT_NONE = 0, MTL_ACT_GELU = 1, MTL_ACT_GELU_GRAD = 2 };
 
 int mtl_abi_version(void);
+/* sizeof(mtl_linear_cfg) as compiled into the library: a binding checks its own struct mirror against it. */
+int mtl_linear_cfg_size(void);
 const char* mtl_last_error(void);
 /* Number of CUDA kernels this library has launched in this process (all threads); bench.py reports the delta over
  * its timed region as `gpu_launches`. */

@@ -45,6 +45,7 @@ _PP = ctypes.POINTER(c_void_p)
 # name -> (restype, argtypes); must list every function include/mtlora_b200.h declares (tests check this).
 SIGNATURES = {
     "mtl_abi_version": (c_int, []),
+    "mtl_linear_cfg_size": (c_int, []),
     "mtl_last_error": (ctypes.c_char_p, []),
     "mtl_launch_count": (c_uint64, []),
     "mtl_linear_rank_pad": (c_int, [_CFG_P]),
@@ -103,6 +104,9 @@ def load():
     got = lib.mtl_abi_version()
     if got != MTL_ABI_VERSION:
         raise RuntimeError(f"libmtlora_b200.so ABI version {got} != expected {MTL_ABI_VERSION}; rebuild")
+    if lib.mtl_linear_cfg_size() != ctypes.sizeof(LinearCfg):
+        raise RuntimeError(f"struct mtl_linear_cfg is {lib.mtl_linear_cfg_size()} bytes in libmtlora_b200.so but "
+                           f"{ctypes.sizeof(LinearCfg)} in the ctypes mirror; rebuild (`make`)")
     _lib = lib
     return lib
 

@@ -110,6 +110,7 @@ using namespace mtl;
 extern "C" {
 
 int mtl_abi_version(void) { return MTL_ABI_VERSION; }
+int mtl_linear_cfg_size(void) { return static_cast<int>(sizeof(mtl_linear_cfg)); }
 const char* mtl_last_error(void) { return g_err; }
 uint64_t mtl_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

@@ -50,6 +50,17 @@ def test_abi_version_and_errors(lib):
     assert nat.mtl_linear_rank_offset(ctypes.byref(cfg), 2) == 32
 
 
+def test_cfg_struct_layout(lib):
+    """The ctypes mirror of struct mtl_linear_cfg has the size the library was compiled with (fields were appended this
+    round: gelu_aux_is_grad, dy_has_sum), and the field offsets follow the C layout rules."""
+    from mtlora_b200 import _native
+    assert lib.mtl_linear_cfg_size() == ctypes.sizeof(_native.LinearCfg)
+    f = _native.LinearCfg
+    assert f.M.offset == 0 and f.in_features.offset == 8 and f.r_task.offset == 32
+    assert f.dropout_seed.offset % 8 == 0 and f.rows_per_sample.offset == f.dropout_seed.offset + 8
+    assert f.dy_has_sum.offset == f.gelu_aux_is_grad.offset + 4 == f.rows_per_sample.offset + 8
+
+
 def test_no_cpu_fallback():
     """The product path must fail loudly on CPU tensors instead of silently computing elsewhere."""
     import torch
