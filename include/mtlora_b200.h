@@ -28,7 +28,9 @@ extern "C" {
 
 typedef void* mtl_stream_t; /* cudaStream_t */
 
-enum { MTL_MODE_MATRIX = 0 }; /* MTLoRALinear shared_mode 'matrix' (models/lora.py:259-266) */
+/* MTLoRALinear shared_mode: 'matrix' (models/lora.py:259-266: task outputs = pretrained + task adapter) and 'matrixv2'
+ * (:267-274: task outputs additionally carry the shared adapter's update). */
+enum { MTL_MODE_MATRIX = 0, MTL_MODE_MATRIXV2 = 1 };
 enum { MTL_ACT_NONE = 0, MTL_ACT_GELU = 1, MTL_ACT_GELU_GRAD = 2 };
 
 int mtl_abi_version(void);
@@ -48,7 +50,7 @@ typedef struct mtl_linear_cfg {
   int32_t out_features;   /* N */
   int32_t n_tasks;        /* T = len(tasks), 0 when the layer was built with tasks=None */
   int32_t x_tasks_given;  /* forward(x, x_tasks) got x_tasks: input is [1+T, M, K] (lora.py:263) */
-  int32_t shared_mode;    /* MTL_MODE_MATRIX */
+  int32_t shared_mode;    /* MTL_MODE_MATRIX or MTL_MODE_MATRIXV2 */
   int32_t r_shared;       /* r['shared']; 0 = no adapters (lora.py:256-257, or CompatLinear) */
   int32_t r_task[MTL_MAX_TASKS];
   float scale_shared;     /* lora_shared_scale */
@@ -85,6 +87,8 @@ int mtl_cast_transpose(const float* w, void* w_bf16, void* wt_bf16, int32_t rows
  *   pre  = x[0] W^T + b
  *   y[0] = pre + s_sh * D(x[0]) A_sh^T B_sh^T
  *   y[t] = pre + s_t  * (x_tasks_given ? x[t] : D(x[0])) A_t^T B_t^T          t = 1..T
+ *   (MTL_MODE_MATRIXV2: y[t] additionally + s_sh * D(x[0]) A_sh^T B_sh^T; in backward the shared adapter then receives
+ *    the gradient of every stream: G_sh = s_sh (sum_j dy[j]) B_sh, dB_sh = (sum_j dy[j])^T U_sh)
  * x:     [S_in, M, K], S_in = 1 (+T if x_tasks_given) (+1 if dropout_p > 0: D(x[0]) appended as last stream,
  *        produced by the upstream kernel with the same seed)
  * y:     [1+T, M, N]  (T = 0 -> a single stream)

@@ -8,7 +8,7 @@ import os
 
 MTL_MAX_TASKS = 7
 MTL_ABI_VERSION = 1
-MTL_MODE_MATRIX = 0
+MTL_MODE_MATRIX, MTL_MODE_MATRIXV2 = 0, 1
 MTL_ACT_NONE, MTL_ACT_GELU, MTL_ACT_GELU_GRAD = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

@@ -43,8 +43,8 @@ int build_layout(const mtl_linear_cfg* c, RankLayout* L) {
   MTL_REQUIRE(c != nullptr, "linear: cfg is NULL");
   MTL_REQUIRE(c->n_tasks >= 0 && c->n_tasks <= MTL_MAX_TASKS, "linear: n_tasks=%d out of range [0, %d]", c->n_tasks,
               MTL_MAX_TASKS);
-  MTL_REQUIRE(c->shared_mode == MTL_MODE_MATRIX, "linear: shared_mode %d not implemented (only 'matrix')",
-              c->shared_mode);
+  MTL_REQUIRE(c->shared_mode == MTL_MODE_MATRIX || c->shared_mode == MTL_MODE_MATRIXV2,
+              "linear: shared_mode %d not implemented ('matrix' and 'matrixv2' are)", c->shared_mode);
   MTL_REQUIRE(c->r_shared >= 0, "linear: negative rank");
   memset(L, 0, sizeof(*L));
   if (c->r_shared == 0) return 0;  // lora.py:256-257: r == 0 -> plain linear, no task outputs
@@ -210,6 +210,10 @@ int mtl_linear_fwd(const mtl_linear_cfg* cfg, const void* x, const void* w_bf16,
     if (lora) {
       p.out_r0[j][0] = L.off[j];
       p.out_len[j][0] = L.len[j];
+      if (j > 0 && cfg->shared_mode == MTL_MODE_MATRIXV2) {   // lora.py:267-274: pretrained + lora (shared) + task adapter
+        p.out_r0[j][1] = L.off[0];
+        p.out_len[j][1] = L.len[0];
+      }
     }
   }
   p.ep_mode = act == MTL_ACT_GELU ? LIN_EP_GELU_DUAL : act == MTL_ACT_GELU_GRAD ? LIN_EP_GELU_DUAL_GRAD : LIN_EP_NONE;
@@ -264,8 +268,21 @@ int mtl_linear_bwd_input(const mtl_linear_cfg* cfg, const void* dy, const void* 
   p.R_pad = L.R_pad;
   int adapter_in[1 + MTL_MAX_TASKS] = {0};
   if (lora) {
+    const bool v2 = cfg->shared_mode == MTL_MODE_MATRIXV2 && L.n > 1;
     for (int a = 0; a < L.n; ++a) {
       adapter_in[a] = a;  // adapter a back-propagates the gradient of output stream a
+      if (a == 0 && v2) {
+        // matrixv2: the shared adapter fed every output stream -> G_sh = s_sh (sum_j dy[j]) B_sh: one group on the
+        // pre-summed stream, or one accumulating group per stream
+        if (dy_sum) {
+          adapter_in[0] = p.S_in - 1;
+          if (int e = add_group(p, p.S_in - 1, L.off[0], L.len[0], 0)) return e;
+        } else {
+          for (int j = 0; j < out_streams(cfg); ++j)
+            if (int e = add_group(p, j, L.off[0], L.len[0], j > 0 ? 1 : 0)) return e;
+        }
+        continue;
+      }
       if (int e = add_group(p, a, L.off[a], L.len[a], 0)) return e;
     }
     fill_granules(p, L, adapter_in);
@@ -339,6 +356,8 @@ int mtl_linear_bwd_params(const mtl_linear_cfg* cfg, const void* x, int32_t x_ge
     MTL_REQUIRE(cfg->rows_per_sample > 0 && M % cfg->rows_per_sample == 0,
                 "linear_bwd_params: rows_per_sample=%d does not divide M=%lld", cfg->rows_per_sample, (long long)M);
   const int n_samples = path_scale != nullptr ? static_cast<int>(M / cfg->rows_per_sample) : 0;
+  MTL_REQUIRE(!((x_gelu || K < 72 || N < 72) && cfg->shared_mode == MTL_MODE_MATRIXV2 && L.n > 1),
+              "linear_bwd_params: matrixv2 needs the tensor-core reduction (no x_gelu, K and N >= 72)");
   if (x_gelu || K < 72 || N < 72) {
     // legacy path (mma.sync): GELU recomputation on load, or operands too narrow for the 128-column UMMA tile
     for (int a = 0; a < L.n; ++a) {
@@ -360,11 +379,26 @@ int mtl_linear_bwd_params(const mtl_linear_cfg* cfg, const void* x, int32_t x_ge
   // one tcgen05 launch for every adapter: wide operands dy (dB) and x (dA), rank operands U and G
   XtyOperand wide[2] = {{dyb, N, 0, out_streams(cfg)}, {xb, K, 0, S_in}};
   XtyOperand rank[2] = {{ub, L.R_pad, 0, 1}, {gb, L.R_pad, 0, 1}};
-  XtyJobGroup grp[2 * (1 + MTL_MAX_TASKS)];
+  XtyJobGroup grp[3 * (1 + MTL_MAX_TASKS)];
   int ng = 0;
-  for (int a = 0; a < L.n; ++a)   // dB_a [N, len] += dy[a]^T (ps[a] * U[:, off:off+len])
+  const bool v2 = cfg->shared_mode == MTL_MODE_MATRIXV2 && L.n > 1;
+  const bool dy_sum = cfg->dy_has_sum != 0 && out_streams(cfg) > 1;
+  if (dy_sum) wide[0].streams += 1;   // dy carries sum_j dy[j] as an extra stream (mtl_scale_rows_sum)
+  for (int a = 0; a < L.n; ++a) {   // dB_a [N, len] += dy[a]^T (ps[a] * U[:, off:off+len])
+    if (a == 0 && v2) {
+      // matrixv2: dB_sh = (sum_j dy[j])^T U_sh — the pre-summed stream, or every stream accumulated by the reduction
+      MTL_REQUIRE(path_scale == nullptr, "linear_bwd_params: matrixv2 with task streams expects pre-scaled dy");
+      if (dy_sum) {
+        grp[ng++] = XtyJobGroup{0, out_streams(cfg), 0, L.off[0], L.len[0], 0, L.R_pad, db_cat, nullptr};
+      } else {
+        for (int j = 0; j < out_streams(cfg); ++j)
+          grp[ng++] = XtyJobGroup{0, j, 0, L.off[0], L.len[0], 0, L.R_pad, db_cat, nullptr};
+      }
+      continue;
+    }
     grp[ng++] = XtyJobGroup{0, a, 0, L.off[a], L.len[a], 0, L.R_pad, db_cat,
                             path_scale ? path_scale + static_cast<size_t>(a) * n_samples : nullptr};
+  }
   if (!xt && (path_scale == nullptr || L.n == 1)) {
     // every adapter consumed the same input stream: dA_cat [R, K] += G^T (ps * x) in one group
     grp[ng++] = XtyJobGroup{1, drop_in, 1, 0, L.R_pad, 1, K, da_cat, path_scale};

@@ -31,7 +31,7 @@ constexpr int XG_ROWS = 64;                 // contraction rows per pipeline sta
 constexpr int XG_BOX_BYTES = XG_ROWS * 128; // one [64 x 64] bf16 box
 constexpr int XG_STAGE_BYTES = 3 * XG_BOX_BYTES;   // wide box 0, wide box 1, rank box
 constexpr int XG_STAGES = 8;
-constexpr int XG_MAX_GROUPS = 20;
+constexpr int XG_MAX_GROUPS = 24;
 constexpr int XG_THREADS = 384;             // 4 control warps, 4 epilogue warps, 4 row-scale warps
 constexpr int XG_TMEM_COLS = 128;           // 2 accumulators x 64 columns
 

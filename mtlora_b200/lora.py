@@ -111,7 +111,8 @@ class LinearEngine:
         _, wt, (_, _, a_cat_t, b_cat_t) = self.stage()
         ps, rps = saved["path_scale"], saved["rows_per_sample"]
         dy_in, dy_sum = dy, False
-        if 1 < spec.S_out < 8 and (ps is not None or spec.K >= 2 * spec.Nf):
+        v2 = spec.mode == ops.N.MTL_MODE_MATRIXV2 and spec.S_out > 1   # shared adapter sees the gradient of every stream
+        if 1 < spec.S_out < 8 and (ps is not None or spec.K >= 2 * spec.Nf or v2):
             # hand the kernel sum_j dy[j] as one extra stream so the frozen product streams one operand tile per column
             # chunk instead of 1+T: worth a pass of its own when there are many chunks (fc2: K = 4 N), free when the
             # DropPath pre-scale pass is needed anyway (it writes the sum along)
@@ -129,9 +130,10 @@ class LinearEngine:
                                      dropout_p=saved["dropout_p"], seed=saved["seed"], save_g=want_ad)
         grads = {}
         if want_ad:
-            da, db = ops.linear_bwd_params(spec, saved["x"], dy, saved["u"], g, x_tasks_given=saved["xt"],
-                                           path_scale=ps, rows_per_sample=rps if ps is not None else 0,
-                                           dropout_p=saved["dropout_p"])
+            da, db = ops.linear_bwd_params(spec, saved["x"], dy_in if (v2 and dy_sum) else dy, saved["u"], g,
+                                           x_tasks_given=saved["xt"], path_scale=ps,
+                                           rows_per_sample=rps if ps is not None else 0, dropout_p=saved["dropout_p"],
+                                           dy_has_sum=v2 and dy_sum)
             T = len(self.tasks)
             for i in range(1 + T):
                 off, r = spec.offsets[i], spec.ranks[i]
@@ -236,9 +238,10 @@ class MTLoRALinear(LoRALayer):
         has_tasks = tasks is not None
         if not has_tasks and shared_mode not in ["matrix"]:
             shared_mode = "matrix"
-        if shared_mode != "matrix":
+        if shared_mode not in ("matrix", "matrixv2"):
             raise NotImplementedError(
-                f"mtlora_b200: shared_mode={shared_mode!r} is not implemented yet (every shipped YAML uses 'matrix')")
+                f"mtlora_b200: shared_mode={shared_mode!r} is not implemented yet ('matrix' — every shipped YAML — and "
+                "'matrixv2' are)")
         if trainable_scale_shared or trainable_scale_per_task:
             raise NotImplementedError("mtlora_b200: trainable LoRA scales are not implemented yet")
         if isinstance(r, int):
@@ -261,7 +264,8 @@ class MTLoRALinear(LoRALayer):
             self.lora_shared_B = nn.Parameter(self.linear.weight.new_zeros((out_features, r["shared"])))
             self.lora_shared_scale = lora_shared_scale
             self.reset_parameters()
-        spec = ops.LinearSpec(in_features, out_features, r["shared"], r_tasks, float(lora_shared_scale), s_tasks)
+        spec = ops.LinearSpec(in_features, out_features, r["shared"], r_tasks, float(lora_shared_scale), s_tasks,
+                              shared_mode=shared_mode if r_tasks else "matrix")
         self._engine = LinearEngine(self, self.linear, spec, tasks if (has_tasks and r["shared"] > 0) else None)
 
     @property

@@ -32,8 +32,12 @@ class LinearSpec:
     CompatLinear, swin_transformer_mtlora.py:36-41), which has a single output stream.
     """
 
-    def __init__(self, in_features, out_features, r_shared=0, r_tasks=(), scale_shared=1.0, scale_tasks=()):
+    def __init__(self, in_features, out_features, r_shared=0, r_tasks=(), scale_shared=1.0, scale_tasks=(),
+                 shared_mode="matrix"):
         self.K, self.Nf = int(in_features), int(out_features)
+        if shared_mode not in ("matrix", "matrixv2"):
+            raise NotImplementedError(f"mtlora_b200: shared_mode={shared_mode!r} is not implemented ('matrix', 'matrixv2' are)")
+        self.mode = N.MTL_MODE_MATRIXV2 if shared_mode == "matrixv2" else N.MTL_MODE_MATRIX
         self.r_shared = int(r_shared)
         self.r_tasks = [int(r) for r in r_tasks] if self.r_shared > 0 else []
         self.T = len(self.r_tasks)
@@ -58,7 +62,7 @@ class LinearSpec:
         c.in_features, c.out_features = self.K, self.Nf
         c.n_tasks = self.T
         c.x_tasks_given = 1 if (x_tasks_given and self.T > 0) else 0
-        c.shared_mode = N.MTL_MODE_MATRIX
+        c.shared_mode = self.mode
         c.r_shared = self.r_shared
         for t in range(self.T):
             c.r_task[t] = self.r_tasks[t]
@@ -163,15 +167,18 @@ def linear_bwd_input(spec, dy, wt_bf16, a_cat_t, b_cat_t, *, x_tasks_given=False
 
 
 def linear_bwd_params(spec, x, dy, u_save, g_save, *, x_tasks_given=False, x_gelu=False, path_scale=None,
-                      rows_per_sample=0, dropout_p=0.0):
-    """-> (da_cat [R, K], db_cat [N, R]) fp32, packed like a_cat / b_cat."""
+                      rows_per_sample=0, dropout_p=0.0, dy_has_sum=False):
+    """-> (da_cat [R, K], db_cat [N, R]) fp32, packed like a_cat / b_cat. dy_has_sum: dy is [S_out + 1, M, N] with the
+    stream sum last (scale_rows_sum); only the matrixv2 mode reads it here."""
     _chk(x, BF16, "x"); _chk(dy, BF16, "dy"); _chk(u_save, BF16, "u_save"); _chk(g_save, BF16, "g_save")
     M = dy.shape[1]
+    if dy.shape[0] != spec.S_out + (1 if dy_has_sum else 0):
+        raise ValueError(f"linear_bwd_params: dy has {dy.shape[0]} streams, expected {spec.S_out + (1 if dy_has_sum else 0)}")
     # one zero-fill for both accumulators
     buf = torch.zeros(spec.R_pad * (spec.K + spec.Nf), dtype=torch.float32, device=dy.device)
     da = buf[:spec.R_pad * spec.K].view(spec.R_pad, spec.K)
     db = buf[spec.R_pad * spec.K:].view(spec.Nf, spec.R_pad)
-    c = spec.cfg(M, x_tasks_given, dropout_p, 0, rows_per_sample)
+    c = spec.cfg(M, x_tasks_given, dropout_p, 0, rows_per_sample, dy_has_sum=dy_has_sum)
     N.call("mtl_linear_bwd_params", ctypes.byref(c), N.ptr(x), 1 if x_gelu else 0, N.ptr(dy), N.ptr(u_save),
            N.ptr(g_save), N.ptr(path_scale), N.ptr(da), N.ptr(db), N.stream(),
            meta=("bwd_params", M, spec.K, spec.Nf, x.shape[0], dy.shape[0], spec.R_pad, sum(spec.ranks), False))

@@ -405,7 +405,7 @@ class _BlockFn(torch.autograd.Function):
         grads = {}
         # fc2 -> d(fc1 pre-activation), GELU' fused into the epilogue
         dg, g2 = e_fc2.backward(sv["sv_2"], dy, gelu_aux=sv["g"], aux_is_grad=True)
-        if dys[0] is None and S > 1 and e_fc2.spec.r_shared > 0:
+        if dys[0] is None and S > 1 and e_fc2.spec.r_shared > 0 and e_fc2.spec.mode == ops.N.MTL_MODE_MATRIX:
             # the shared output stream is unused downstream (last stage, reference quirk: its fc2.lora_shared_{A,B}
             # receive no gradient at all) -> report None like autograd does, not zeros
             fc2 = blk.mlp.fc2

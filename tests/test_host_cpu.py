@@ -98,7 +98,13 @@ def test_cpu_inputs_raise_loudly():
 def test_unsupported_modes_raise():
     from mtlora_b200.lora import MTLoRALinear
     with pytest.raises(NotImplementedError):
-        MTLoRALinear(8, 8, r={"shared": 4, "a": 4}, tasks=["a"], lora_task_scale={"a": 1.0}, shared_mode="matrixv2")
+        MTLoRALinear(8, 8, r={"shared": 4, "a": 4}, tasks=["a"], lora_task_scale={"a": 1.0}, shared_mode="addition")
+    with pytest.raises(NotImplementedError):
+        MTLoRALinear(8, 8, r=4, trainable_scale_shared=True)
+    m = MTLoRALinear(8, 8, r={"shared": 4, "a": 4}, tasks=["a"], lora_task_scale={"a": 1.0}, shared_mode="matrixv2")
+    assert m.shared_mode == "matrixv2" and m.engine.spec.cfg(1, False).shared_mode == 1   # MTL_MODE_MATRIXV2
+    # without tasks the reference falls back to 'matrix' (lora.py:183-186)
+    assert MTLoRALinear(8, 8, r=4, shared_mode="matrixv2").shared_mode == "matrix"
     with pytest.raises(AssertionError):
         MTLoRALinear(8, 8, r=4, shared_mode="bogus")
 

@@ -61,17 +61,20 @@ def quiet(fn, *a, **k):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("tag,K,N,r,use_tasks,xt", [
-    ("lin_shared", 96, 288, {"shared": 8}, False, False),
-    ("lin_tasks", 96, 96, {"shared": 16, "normals": 4, "semseg": 4}, True, False),
-    ("lin_xtasks", 96, 384, {"shared": 16, "normals": 4, "semseg": 8}, True, True),
-    ("lin_r0", 64, 48, {"shared": 0}, False, False),
+@pytest.mark.parametrize("tag,K,N,r,use_tasks,xt,mode", [
+    ("lin_shared", 96, 288, {"shared": 8}, False, False, "matrix"),
+    ("lin_tasks", 96, 96, {"shared": 16, "normals": 4, "semseg": 4}, True, False, "matrix"),
+    ("lin_xtasks", 96, 384, {"shared": 16, "normals": 4, "semseg": 8}, True, True, "matrix"),
+    ("lin_r0", 64, 48, {"shared": 0}, False, False, "matrix"),
+    ("lin_v2_tasks", 96, 96, {"shared": 16, "normals": 4, "semseg": 4}, True, False, "matrixv2"),
+    ("lin_v2_xtasks", 96, 384, {"shared": 16, "normals": 4, "semseg": 8}, True, True, "matrixv2"),
 ])
-def test_mtlora_linear_module(S, golden, tag, K, N, r, use_tasks, xt):
-    """MTLoRALinear module API (models/lora.py:161-284) vs the reference's own outputs / gradients."""
+def test_mtlora_linear_module(S, golden, tag, K, N, r, use_tasks, xt, mode):
+    """MTLoRALinear module API (models/lora.py:161-284; shared_mode 'matrix' and 'matrixv2') vs the reference's own
+    outputs / gradients."""
     from mtlora_b200.lora import MTLoRALinear
     m = MTLoRALinear(K, N, r=r, lora_shared_scale=4.0, lora_task_scale={t: 2.0 + i for i, t in enumerate(TASKS)},
-                     lora_dropout=0.0, tasks=TASKS if use_tasks else None)
+                     lora_dropout=0.0, tasks=TASKS if use_tasks else None, shared_mode=mode)
     load_det(m, tag + ".")
     m.cuda()
     x = detgen.uniform(tag + ".x", (2, 49, K)).cuda().requires_grad_()

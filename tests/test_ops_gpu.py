@@ -178,6 +178,43 @@ def test_linear_fwd_bwd(ops, tag, M, K, N, r_s, r_t, xt, gelu, res, pscale):
             assert da[~valid].abs().max().item() == 0 and db[:, ~valid].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("xt,presum", [(True, True), (True, False), (False, True)])
+def test_linear_matrixv2(ops, xt, presum):
+    """shared_mode 'matrixv2' (lora.py:267-274): task outputs = pretrained + shared adapter + task adapter; the shared
+    adapter's gradients then sum over every stream (pre-summed stream or accumulating groups)."""
+    M, K, N, T = 3000, 192, 384, 3
+    tasks = [f"t{i}" for i in range(T)]
+    spec = ops.LinearSpec(K, N, 16, [4, 8, 4], 4.0, [2.0, 3.0, 4.0], shared_mode="matrixv2")
+    p = {"linear.weight": dev(detgen.uniform("v2.w", (N, K), -0.05, 0.05)), "linear.bias": dev(detgen.uniform("v2.b", (N,))),
+         "lora_shared_A": dev(detgen.uniform("v2.as", (16, K), -0.1, 0.1)), "lora_shared_B": dev(detgen.uniform("v2.bs", (N, 16), -0.1, 0.1))}
+    for i, t in enumerate(tasks):
+        p["lora_tasks_A." + t] = dev(detgen.uniform("v2.at" + t, (spec.r_tasks[i], K), -0.1, 0.1))
+        p["lora_tasks_B." + t] = dev(detgen.uniform("v2.bt" + t, (N, spec.r_tasks[i]), -0.1, 0.1))
+    tscale = {t: spec.scale_tasks[i] for i, t in enumerate(tasks)}
+    wb, wt = ops.cast_transpose(p["linear.weight"])
+    a_cat, b_cat, a_cat_t, b_cat_t = ops.pack_adapters(spec, p["lora_shared_A"], p["lora_shared_B"],
+                                                       [p["lora_tasks_A." + t] for t in tasks], [p["lora_tasks_B." + t] for t in tasks])
+    S_in = 1 + (T if xt else 0)
+    x = bf(dev(detgen.uniform("v2.x", (S_in, M, K))))
+    y, _, u = ops.linear_fwd(spec, x, wb, p["linear.bias"], a_cat, b_cat, x_tasks_given=xt, save_u=True)
+    pr = {k: v.clone().requires_grad_() for k, v in p.items()}
+    xf = x.float().requires_grad_()
+    ys, yt = O.mtlora_linear(pr, "", xf[0], {t: xf[1 + i] for i, t in enumerate(tasks)} if xt else None, tasks, 4.0, tscale,
+                             mode="matrixv2")
+    ref = torch.stack([ys] + [yt[t] for t in tasks])
+    check(y, ref, what="y (matrixv2)")
+    dy = bf(dev(detgen.uniform("v2.dy", (1 + T, M, N))))
+    (ref * dy.float()).sum().backward()
+    dy_in = ops.scale_rows_sum(dy, None, 0) if presum else dy
+    dx, g = ops.linear_bwd_input(spec, dy_in, wt, a_cat_t, b_cat_t, x_tasks_given=xt, dy_has_sum=presum, save_g=True)
+    check(dx, xf.grad, what="dx (matrixv2)")
+    da, db = ops.linear_bwd_params(spec, x, dy_in, u, g, x_tasks_given=xt, dy_has_sum=presum)
+    names = [("lora_shared_A", "lora_shared_B")] + [("lora_tasks_A." + t, "lora_tasks_B." + t) for t in tasks]
+    for (ka, kb), off, r in zip(names, spec.offsets, spec.ranks):
+        check(da[off:off + r], pr[ka].grad, tol=2e-2, what="d" + ka)
+        check(db[:, off:off + r], pr[kb].grad, tol=2e-2, what="d" + kb)
+
+
 def test_linear_gelu_bwd_aux(ops):
     """fc2 input gradient fused with GELU'(fc1 pre-activation) (Mlp.forward :69-77 in reverse)."""
     M, K, N = 392, 384, 96

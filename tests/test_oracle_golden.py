@@ -35,17 +35,19 @@ def lin_shapes(K, N, r, tasks):
     return s
 
 
-@pytest.mark.parametrize("tag,K,N,r,use_tasks,xt", [
-    ("lin_shared", 96, 288, {"shared": 8}, False, False),
-    ("lin_tasks", 96, 96, {"shared": 16, "normals": 4, "semseg": 4}, True, False),
-    ("lin_xtasks", 96, 384, {"shared": 16, "normals": 4, "semseg": 8}, True, True),
-    ("lin_r0", 64, 48, {"shared": 0}, False, False),
+@pytest.mark.parametrize("tag,K,N,r,use_tasks,xt,mode", [
+    ("lin_shared", 96, 288, {"shared": 8}, False, False, "matrix"),
+    ("lin_tasks", 96, 96, {"shared": 16, "normals": 4, "semseg": 4}, True, False, "matrix"),
+    ("lin_xtasks", 96, 384, {"shared": 16, "normals": 4, "semseg": 8}, True, True, "matrix"),
+    ("lin_r0", 64, 48, {"shared": 0}, False, False, "matrix"),
+    ("lin_v2_tasks", 96, 96, {"shared": 16, "normals": 4, "semseg": 4}, True, False, "matrixv2"),
+    ("lin_v2_xtasks", 96, 384, {"shared": 16, "normals": 4, "semseg": 8}, True, True, "matrixv2"),
 ])
-def test_mtlora_linear(golden, tag, K, N, r, use_tasks, xt):
+def test_mtlora_linear(golden, tag, K, N, r, use_tasks, xt, mode):
     p = det_module_params(tag, lin_shapes(K, N, r, TASKS if use_tasks else None))
     x = detgen.uniform(tag + ".x", (2, 49, K)).requires_grad_()
     x_tasks = {t: detgen.uniform(f"{tag}.x.{t}", (2, 49, K)).requires_grad_() for t in TASKS} if xt else None
-    y, yt = O.mtlora_linear(p, "", x, x_tasks, TASKS if use_tasks else None, 4.0, TSCALE)
+    y, yt = O.mtlora_linear(p, "", x, x_tasks, TASKS if use_tasks else None, 4.0, TSCALE, mode=mode)
     loss = (y * detgen.uniform(tag + ".gy", tuple(y.shape))).sum()
     if use_tasks:
         assert yt is not None and list(yt) == TASKS

@@ -86,14 +86,16 @@ def main():
 
     # ---- 1. MTLoRALinear (models/lora.py:159-284) --------------------------------------------------------------
     tasks = ["normals", "semseg"]
-    for tag, K, N, r, use_tasks, xt in [
-        ("lin_shared", 96, 288, {"shared": 8}, False, False),
-        ("lin_tasks", 96, 96, {"shared": 16, "normals": 4, "semseg": 4}, True, False),
-        ("lin_xtasks", 96, 384, {"shared": 16, "normals": 4, "semseg": 8}, True, True),
-        ("lin_r0", 64, 48, {"shared": 0}, False, False),
+    for tag, K, N, r, use_tasks, xt, mode in [
+        ("lin_shared", 96, 288, {"shared": 8}, False, False, "matrix"),
+        ("lin_tasks", 96, 96, {"shared": 16, "normals": 4, "semseg": 4}, True, False, "matrix"),
+        ("lin_xtasks", 96, 384, {"shared": 16, "normals": 4, "semseg": 8}, True, True, "matrix"),
+        ("lin_r0", 64, 48, {"shared": 0}, False, False, "matrix"),
+        ("lin_v2_tasks", 96, 96, {"shared": 16, "normals": 4, "semseg": 4}, True, False, "matrixv2"),   # lora.py:267-274
+        ("lin_v2_xtasks", 96, 384, {"shared": 16, "normals": 4, "semseg": 8}, True, True, "matrixv2"),
     ]:
         m = MTLoRALinear(K, N, r=r, lora_shared_scale=4.0, lora_task_scale={t: 2.0 + i for i, t in enumerate(tasks)},
-                         lora_dropout=0.0, tasks=tasks if use_tasks else None)
+                         lora_dropout=0.0, tasks=tasks if use_tasks else None, shared_mode=mode)
         load_det(m, tag + ".")
         x = detgen.uniform(tag + ".x", (2, 49, K)).requires_grad_()
         x_tasks = {t: detgen.uniform(f"{tag}.x.{t}", (2, 49, K)).requires_grad_() for t in tasks} if xt else None
