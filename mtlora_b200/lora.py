@@ -61,10 +61,24 @@ class LinearEngine:
         ps += [o.lora_tasks_A[t] for t in self.tasks] + [o.lora_tasks_B[t] for t in self.tasks]
         return ps
 
+    def scales(self):
+        """Trainable LoRA scales (lora.py:210-216, 229-233) as (adapter index, Parameter) pairs: 0 = shared, 1+t = task."""
+        o = self.owner
+        if o is None or self.spec.r_shared == 0:
+            return []
+        out = []
+        if isinstance(getattr(o, "lora_shared_scale", None), nn.Parameter):
+            out.append((0, o.lora_shared_scale))
+        ts = getattr(o, "lora_task_scale", None)
+        if isinstance(ts, nn.ParameterDict):
+            out += [(1 + i, ts[t]) for i, t in enumerate(self.tasks)]
+        return out
+
     def params(self):
-        """Parameters in the order `backward` reports gradients: weight, bias?, shared A, B, task A..., task B..."""
+        """Parameters in the order `backward` reports gradients: weight, bias?, shared A, B, task A..., task B..., scales."""
         lin = self.linear
-        return [lin.weight] + ([lin.bias] if lin.bias is not None else []) + self.adapters()
+        return ([lin.weight] + ([lin.bias] if lin.bias is not None else []) + self.adapters()
+                + [p for _, p in self.scales()])
 
     def stage(self):
         w = self.linear.weight
@@ -77,11 +91,17 @@ class LinearEngine:
             self._wkey = key
         if self.spec.r_shared > 0:
             ad = self.adapters()
-            akey = tuple((p.data_ptr(), p._version) for p in ad)
+            sc = self.scales()
+            akey = tuple((p.data_ptr(), p._version) for p in ad + [q for _, q in sc])
             if akey != self._akey:
                 T = len(self.tasks)
                 with torch.no_grad():
                     d = [p.detach().float().contiguous() for p in ad]
+                    # a trainable scale is folded into the packed B operand (the kernels then run with scale 1): no
+                    # device -> host read of the parameter, forward / input gradient / dA exact as they stand
+                    for i, q in sc:
+                        j = 1 if i == 0 else 2 + T + (i - 1)
+                        d[j] = d[j] * q.detach().float()
                     self._packed = ops.pack_adapters(self.spec, d[0], d[1], d[2:2 + T], d[2 + T:2 + 2 * T])
                 self._akey = akey
         return self._w, self._wt, self._packed
@@ -135,14 +155,22 @@ class LinearEngine:
                                            rows_per_sample=rps if ps is not None else 0, dropout_p=saved["dropout_p"],
                                            dy_has_sum=v2 and dy_sum)
             T = len(self.tasks)
+            tscale = dict(self.scales())
             for i in range(1 + T):
                 off, r = spec.offsets[i], spec.ranks[i]
                 pa = ad[0] if i == 0 else ad[2 + (i - 1)]
                 pb = ad[1] if i == 0 else ad[2 + T + (i - 1)]
                 if pa.requires_grad:
                     grads[pa] = da[off:off + r]
+                dbi = db[:, off:off + r]
+                if i in tscale:
+                    # the kernels ran with scale 1 on U = x A^T: db = dy^T U, so dB = s db and ds = <db, B>
+                    q = tscale[i]
+                    if q.requires_grad:
+                        grads[q] = (dbi * pb.detach().float()).sum().reshape(1)
+                    dbi = dbi * q.detach().float()
                 if pb.requires_grad:
-                    grads[pb] = db[:, off:off + r]
+                    grads[pb] = dbi
         if lin.weight.requires_grad or (lin.bias is not None and lin.bias.requires_grad):
             # trainable dense weight (PatchMerging.reduction under plain MTLoRA, lora.py:599-600; or an unfrozen layer):
             # dW = dPre^T x[0], dbias = column sums of dPre, dPre = sum_j dy[j] (lora.py:255,262-266)
@@ -242,8 +270,6 @@ class MTLoRALinear(LoRALayer):
             raise NotImplementedError(
                 f"mtlora_b200: shared_mode={shared_mode!r} is not implemented yet ('matrix' — every shipped YAML — and "
                 "'matrixv2' are)")
-        if trainable_scale_shared or trainable_scale_per_task:
-            raise NotImplementedError("mtlora_b200: trainable LoRA scales are not implemented yet")
         if isinstance(r, int):
             r = {"shared": r}
         super().__init__(r=r["shared"], lora_alpha=lora_shared_scale, lora_dropout=lora_dropout)
@@ -257,14 +283,25 @@ class MTLoRALinear(LoRALayer):
                     task: nn.Parameter(self.linear.weight.new_zeros((r[task], in_features))) for task in tasks})
                 self.lora_tasks_B = nn.ParameterDict({
                     task: nn.Parameter(self.linear.weight.new_zeros((out_features, r[task]))) for task in tasks})
-                self.lora_task_scale = {task: lora_task_scale[task] for task in tasks}
+                if trainable_scale_per_task:
+                    # reference :210-214 (it takes a float here; a per-task mapping is accepted too)
+                    init = lora_task_scale if isinstance(lora_task_scale, Mapping) else {t: lora_task_scale for t in tasks}
+                    self.lora_task_scale = nn.ParameterDict({
+                        task: nn.Parameter(torch.FloatTensor([float(init[task])])) for task in tasks})
+                    s_tasks = [1.0] * len(tasks)      # folded into the packed B operand (LinearEngine.stage)
+                else:
+                    self.lora_task_scale = {task: lora_task_scale[task] for task in tasks}
+                    s_tasks = [float(self.lora_task_scale[t]) for t in tasks]
                 r_tasks = [r[t] for t in tasks]
-                s_tasks = [float(self.lora_task_scale[t]) for t in tasks]
             self.lora_shared_A = nn.Parameter(self.linear.weight.new_zeros((r["shared"], in_features)))
             self.lora_shared_B = nn.Parameter(self.linear.weight.new_zeros((out_features, r["shared"])))
-            self.lora_shared_scale = lora_shared_scale
+            if trainable_scale_shared:
+                self.lora_shared_scale = nn.Parameter(torch.FloatTensor([float(lora_shared_scale)]))   # reference :229-231
+            else:
+                self.lora_shared_scale = lora_shared_scale
             self.reset_parameters()
-        spec = ops.LinearSpec(in_features, out_features, r["shared"], r_tasks, float(lora_shared_scale), s_tasks,
+        spec = ops.LinearSpec(in_features, out_features, r["shared"], r_tasks,
+                              1.0 if (trainable_scale_shared and r["shared"] > 0) else float(lora_shared_scale), s_tasks,
                               shared_mode=shared_mode if r_tasks else "matrix")
         self._engine = LinearEngine(self, self.linear, spec, tasks if (has_tasks and r["shared"] > 0) else None)
 

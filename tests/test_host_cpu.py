@@ -99,8 +99,13 @@ def test_unsupported_modes_raise():
     from mtlora_b200.lora import MTLoRALinear
     with pytest.raises(NotImplementedError):
         MTLoRALinear(8, 8, r={"shared": 4, "a": 4}, tasks=["a"], lora_task_scale={"a": 1.0}, shared_mode="addition")
-    with pytest.raises(NotImplementedError):
-        MTLoRALinear(8, 8, r=4, trainable_scale_shared=True)
+    ts = MTLoRALinear(8, 8, r={"shared": 4, "a": 4}, tasks=["a"], lora_task_scale=2.5, lora_shared_scale=4.0,
+                      trainable_scale_shared=True, trainable_scale_per_task=True)
+    # same registration order as the reference (direct parameters first, then linear, the task dicts, the scale dict)
+    assert [n for n, _ in ts.named_parameters()] == ["lora_shared_A", "lora_shared_B", "lora_shared_scale", "linear.weight",
+                                                      "linear.bias", "lora_tasks_A.a", "lora_tasks_B.a", "lora_task_scale.a"]
+    assert float(ts.lora_shared_scale) == 4.0 and float(ts.lora_task_scale["a"]) == 2.5
+    assert ts.engine.spec.scale_shared == 1.0 and ts.engine.spec.scale_tasks == [1.0]   # folded into the packed B
     m = MTLoRALinear(8, 8, r={"shared": 4, "a": 4}, tasks=["a"], lora_task_scale={"a": 1.0}, shared_mode="matrixv2")
     assert m.shared_mode == "matrixv2" and m.engine.spec.cfg(1, False).shared_mode == 1   # MTL_MODE_MATRIXV2
     # without tasks the reference falls back to 'matrix' (lora.py:183-186)

@@ -68,13 +68,18 @@ def quiet(fn, *a, **k):
     ("lin_r0", 64, 48, {"shared": 0}, False, False, "matrix"),
     ("lin_v2_tasks", 96, 96, {"shared": 16, "normals": 4, "semseg": 4}, True, False, "matrixv2"),
     ("lin_v2_xtasks", 96, 384, {"shared": 16, "normals": 4, "semseg": 8}, True, True, "matrixv2"),
+    ("lin_tscale", 96, 192, {"shared": 16, "normals": 4, "semseg": 8}, True, True, "matrix+trainable_scales"),
 ])
 def test_mtlora_linear_module(S, golden, tag, K, N, r, use_tasks, xt, mode):
     """MTLoRALinear module API (models/lora.py:161-284; shared_mode 'matrix' and 'matrixv2') vs the reference's own
     outputs / gradients."""
     from mtlora_b200.lora import MTLoRALinear
-    m = MTLoRALinear(K, N, r=r, lora_shared_scale=4.0, lora_task_scale={t: 2.0 + i for i, t in enumerate(TASKS)},
-                     lora_dropout=0.0, tasks=TASKS if use_tasks else None, shared_mode=mode)
+    trainable = mode.endswith("+trainable_scales")   # lora.py:210-216, 229-233: the scales are Parameters
+    mode = mode.split("+")[0]
+    m = MTLoRALinear(K, N, r=r, lora_shared_scale=4.0,
+                     lora_task_scale=2.5 if trainable else {t: 2.0 + i for i, t in enumerate(TASKS)},
+                     lora_dropout=0.0, tasks=TASKS if use_tasks else None, shared_mode=mode,
+                     trainable_scale_shared=trainable, trainable_scale_per_task=trainable)
     load_det(m, tag + ".")
     m.cuda()
     x = detgen.uniform(tag + ".x", (2, 49, K)).cuda().requires_grad_()

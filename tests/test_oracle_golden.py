@@ -42,12 +42,22 @@ def lin_shapes(K, N, r, tasks):
     ("lin_r0", 64, 48, {"shared": 0}, False, False, "matrix"),
     ("lin_v2_tasks", 96, 96, {"shared": 16, "normals": 4, "semseg": 4}, True, False, "matrixv2"),
     ("lin_v2_xtasks", 96, 384, {"shared": 16, "normals": 4, "semseg": 8}, True, True, "matrixv2"),
+    ("lin_tscale", 96, 192, {"shared": 16, "normals": 4, "semseg": 8}, True, True, "matrix+trainable_scales"),
 ])
 def test_mtlora_linear(golden, tag, K, N, r, use_tasks, xt, mode):
-    p = det_module_params(tag, lin_shapes(K, N, r, TASKS if use_tasks else None))
+    trainable = mode.endswith("+trainable_scales")
+    mode = mode.split("+")[0]
+    shapes = lin_shapes(K, N, r, TASKS if use_tasks else None)
+    if trainable:   # the scales are parameters of the module (lora.py:210-216, 229-233), filled like every other one
+        shapes["lora_shared_scale"] = (1,)
+        for t in TASKS:
+            shapes["lora_task_scale." + t] = (1,)
+    p = det_module_params(tag, shapes)
     x = detgen.uniform(tag + ".x", (2, 49, K)).requires_grad_()
     x_tasks = {t: detgen.uniform(f"{tag}.x.{t}", (2, 49, K)).requires_grad_() for t in TASKS} if xt else None
-    y, yt = O.mtlora_linear(p, "", x, x_tasks, TASKS if use_tasks else None, 4.0, TSCALE, mode=mode)
+    sc_sh = p["lora_shared_scale"] if trainable else 4.0
+    sc_t = {t: p["lora_task_scale." + t] for t in TASKS} if trainable else TSCALE
+    y, yt = O.mtlora_linear(p, "", x, x_tasks, TASKS if use_tasks else None, sc_sh, sc_t, mode=mode)
     loss = (y * detgen.uniform(tag + ".gy", tuple(y.shape))).sum()
     if use_tasks:
         assert yt is not None and list(yt) == TASKS

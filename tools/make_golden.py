@@ -93,9 +93,16 @@ def main():
         ("lin_r0", 64, 48, {"shared": 0}, False, False, "matrix"),
         ("lin_v2_tasks", 96, 96, {"shared": 16, "normals": 4, "semseg": 4}, True, False, "matrixv2"),   # lora.py:267-274
         ("lin_v2_xtasks", 96, 384, {"shared": 16, "normals": 4, "semseg": 8}, True, True, "matrixv2"),
+        # trainable scales (lora.py:210-216, 229-233): Parameters initialised to the given floats; the reference needs a
+        # FLOAT lora_task_scale in this mode (torch.FloatTensor([lora_task_scale]))
+        ("lin_tscale", 96, 192, {"shared": 16, "normals": 4, "semseg": 8}, True, True, "matrix+trainable_scales"),
     ]:
-        m = MTLoRALinear(K, N, r=r, lora_shared_scale=4.0, lora_task_scale={t: 2.0 + i for i, t in enumerate(tasks)},
-                         lora_dropout=0.0, tasks=tasks if use_tasks else None, shared_mode=mode)
+        trainable = mode.endswith("+trainable_scales")
+        mode = mode.split("+")[0]
+        m = MTLoRALinear(K, N, r=r, lora_shared_scale=4.0,
+                         lora_task_scale=2.5 if trainable else {t: 2.0 + i for i, t in enumerate(tasks)},
+                         lora_dropout=0.0, tasks=tasks if use_tasks else None, shared_mode=mode,
+                         trainable_scale_shared=trainable, trainable_scale_per_task=trainable)
         load_det(m, tag + ".")
         x = detgen.uniform(tag + ".x", (2, 49, K)).requires_grad_()
         x_tasks = {t: detgen.uniform(f"{tag}.x.{t}", (2, 49, K)).requires_grad_() for t in tasks} if xt else None
