@@ -96,9 +96,8 @@ struct AttnParams {
 };
 
 __global__ void __launch_bounds__(128, 4) win_attn_fwd_kernel(const AttnParams p) {
-  __shared__ __align__(16) __nv_bfloat16 Qs[NP * QS];
-  __shared__ __align__(16) __nv_bfloat16 Ks[NP * QS];
-  __shared__ __align__(16) __nv_bfloat16 Vs[NP * QS];
+  // q / k / v tiles are double-buffered: the gather of the CTA's next window runs under the math of the current one
+  __shared__ __align__(16) __nv_bfloat16 QKV[2][3][NP * QS];
   __shared__ float bias_s[225];
   __shared__ int2 tok_yx[NP];   // (row, column) of every window token: one division per token per CTA, not per pair
   __shared__ __align__(8) int reg_s[NP];
@@ -146,39 +145,55 @@ __global__ void __launch_bounds__(128, 4) win_attn_fwd_kernel(const AttnParams p
   const int tok_a = threadIdx.x >> 2, tok_b = tok_a + 32;
   const int ay = tok_a / g.ws, ax = tok_a - ay * g.ws, by = tok_b / g.ws, bx = tok_b - by * g.ws;
   const bool a_ok = tok_a < g.N, b_ok = tok_b < g.N;
-  const uint32_t q_a = smem_u32(Qs + tok_a * QS + ch8), q_b = smem_u32(Qs + tok_b * QS + ch8);
+  // token (within window) -> row of the token matrix for window `win`, cyclic shift folded in
+  auto rows_of = [&](int win, int& ra, int& rb) {
+    const int b = win / nW, wi = win - b * nW;
+    const int wy = wi / g.nww, wx = wi - wy * g.nww;
+    int r = wy * g.ws + ay + g.shift, c = wx * g.ws + ax + g.shift;
+    if (r >= g.H) r -= g.H;
+    if (c >= g.W) c -= g.W;
+    ra = (b * g.H + r) * g.W + c;
+    r = wy * g.ws + by + g.shift; c = wx * g.ws + bx + g.shift;
+    if (r >= g.H) r -= g.H;
+    if (c >= g.W) c -= g.W;
+    rb = (b * g.H + r) * g.W + c;
+  };
+  // gather q,k,v rows of this head into buffer `bi`: 3 tiles x 2 rows x one 16-byte chunk per thread
+  auto gather = [&](int bi, int ra, int rb) {
+    const __nv_bfloat16* sa = p.qkv + static_cast<size_t>(a_ok ? ra : 0) * C3 + head * HD + ch8;
+    const __nv_bfloat16* sb = p.qkv + static_cast<size_t>(b_ok ? rb : 0) * C3 + head * HD + ch8;
+#pragma unroll
+    for (int w3 = 0; w3 < 3; ++w3) {
+      cp_async_16_zfill(smem_u32(QKV[bi][w3] + tok_a * QS + ch8), sa + w3 * p.C, a_ok);
+      cp_async_16_zfill(smem_u32(QKV[bi][w3] + tok_b * QS + ch8), sb + w3 * p.C, b_ok);
+    }
+    cp_async_commit();
+  };
 
-  for (int win = blockIdx.x; win < n_win; win += gridDim.x) {
+  int buf = 0;
+  int ra = 0, rb = 0, ra_n = 0, rb_n = 0;
+  if (static_cast<int>(blockIdx.x) < n_win) {
+    rows_of(blockIdx.x, ra, rb);
+    gather(0, ra, rb);
+  }
+  for (int win = blockIdx.x; win < n_win; win += gridDim.x, buf ^= 1, ra = ra_n, rb = rb_n) {
     const int b = win / nW, wi = win - b * nW;
     const int wy = wi / g.nww, wx = wi - wy * g.nww;
     // only windows in the last window row / column straddle the shift seam (:297-319)
     const bool seam = p.mask == nullptr && g.shift > 0 && (wy == g.nwh - 1 || wx == g.nww - 1);
-    int ra, rb;
-    {
-      int r = wy * g.ws + ay + g.shift, c = wx * g.ws + ax + g.shift;
-      if (r >= g.H) r -= g.H;
-      if (c >= g.W) c -= g.W;
-      ra = (b * g.H + r) * g.W + c;
-      r = wy * g.ws + by + g.shift; c = wx * g.ws + bx + g.shift;
-      if (r >= g.H) r -= g.H;
-      if (c >= g.W) c -= g.W;
-      rb = (b * g.H + r) * g.W + c;
-    }
-    __syncthreads();  // previous iteration done with smem
+    __nv_bfloat16* Qs = QKV[buf][0];
+    __nv_bfloat16* Ks = QKV[buf][1];
+    __nv_bfloat16* Vs = QKV[buf][2];
+    __syncthreads();  // previous iteration done with the other buffer (its output staging) and with reg_s
     if (seam && threadIdx.x < NP) reg_s[threadIdx.x] = threadIdx.x < g.N ? region_id(g, wy, wx, threadIdx.x) : 0;
-    {
-      // gather q,k,v rows of this head: 3 tiles x 2 rows x one 16-byte chunk per thread
-      const __nv_bfloat16* sa = p.qkv + static_cast<size_t>(a_ok ? ra : 0) * C3 + head * HD + ch8;
-      const __nv_bfloat16* sb = p.qkv + static_cast<size_t>(b_ok ? rb : 0) * C3 + head * HD + ch8;
-      cp_async_16_zfill(q_a, sa, a_ok);
-      cp_async_16_zfill(q_b, sb, b_ok);
-      cp_async_16_zfill(smem_u32(Ks + tok_a * QS + ch8), sa + p.C, a_ok);
-      cp_async_16_zfill(smem_u32(Ks + tok_b * QS + ch8), sb + p.C, b_ok);
-      cp_async_16_zfill(smem_u32(Vs + tok_a * QS + ch8), sa + 2 * p.C, a_ok);
-      cp_async_16_zfill(smem_u32(Vs + tok_b * QS + ch8), sb + 2 * p.C, b_ok);
+    const int next = win + gridDim.x;
+    if (next < n_win) {
+      rows_of(next, ra_n, rb_n);
+      gather(buf ^ 1, ra_n, rb_n);
+      cp_async_wait<1>();   // this window's tiles have landed; the next window's are in flight
+    } else {
+      cp_async_wait<0>();
     }
-    cp_async_commit();
-    cp_async_wait<0>();
     __syncthreads();
 
     float s[8][4];
@@ -305,13 +320,15 @@ struct AttnBwdParams {
   WinGeom g;
 };
 
+constexpr int kBwdTile = NP * QS;                 // one [64 x 32] tile (padded rows), in bf16 elements
+constexpr int kBwdSmemBytes = (2 * 4 * kBwdTile + 2 * NP * PS) * 2;   // q,k,v,dO double-buffered + P, dS
+
 __global__ void __launch_bounds__(128, 3) win_attn_bwd_kernel(const AttnBwdParams p) {
-  __shared__ __align__(16) __nv_bfloat16 Qs[NP * QS];
-  __shared__ __align__(16) __nv_bfloat16 Ks[NP * QS];
-  __shared__ __align__(16) __nv_bfloat16 Vs[NP * QS];
-  __shared__ __align__(16) __nv_bfloat16 dOs[NP * QS];
-  __shared__ __align__(16) __nv_bfloat16 Ps[NP * PS];
-  __shared__ __align__(16) __nv_bfloat16 dSs[NP * PS];
+  // q / k / v / dO tiles are double-buffered (dynamic shared memory): the gather of the CTA's next window runs under the
+  // math of the current one
+  extern __shared__ __align__(16) __nv_bfloat16 bwd_smem[];
+  __nv_bfloat16* const Ps = bwd_smem + 2 * 4 * kBwdTile;
+  __nv_bfloat16* const dSs = Ps + NP * PS;
   __shared__ float bias_s[225];
   __shared__ int2 tok_yx[NP];   // (row, column) of every window token: one division per token per CTA, not per pair
   __shared__ float dbias_s[225];
@@ -363,38 +380,57 @@ __global__ void __launch_bounds__(128, 3) win_attn_bwd_kernel(const AttnBwdParam
   const int ay = tok_a / g.ws, ax = tok_a - ay * g.ws, by = tok_b / g.ws, bx = tok_b - by * g.ws;
   const bool a_ok = tok_a < g.N, b_ok = tok_b < g.N;
 
-  for (int win = blockIdx.x; win < n_win; win += gridDim.x) {
+  auto rows_of = [&](int win, int& ra, int& rb) {
+    const int b = win / nW, wi = win - b * nW;
+    const int wy = wi / g.nww, wx = wi - wy * g.nww;
+    int r = wy * g.ws + ay + g.shift, c = wx * g.ws + ax + g.shift;
+    if (r >= g.H) r -= g.H;
+    if (c >= g.W) c -= g.W;
+    ra = (b * g.H + r) * g.W + c;
+    r = wy * g.ws + by + g.shift; c = wx * g.ws + bx + g.shift;
+    if (r >= g.H) r -= g.H;
+    if (c >= g.W) c -= g.W;
+    rb = (b * g.H + r) * g.W + c;
+  };
+  auto gather = [&](int bi, int ra, int rb) {
+    __nv_bfloat16* t0 = bwd_smem + bi * 4 * kBwdTile;
+    const size_t oa = static_cast<size_t>(a_ok ? ra : 0), ob = static_cast<size_t>(b_ok ? rb : 0);
+    const __nv_bfloat16* sa = p.qkv + oa * C3 + head * HD + ch8;
+    const __nv_bfloat16* sb = p.qkv + ob * C3 + head * HD + ch8;
+#pragma unroll
+    for (int w3 = 0; w3 < 3; ++w3) {
+      cp_async_16_zfill(smem_u32(t0 + w3 * kBwdTile + tok_a * QS + ch8), sa + w3 * p.C, a_ok);
+      cp_async_16_zfill(smem_u32(t0 + w3 * kBwdTile + tok_b * QS + ch8), sb + w3 * p.C, b_ok);
+    }
+    cp_async_16_zfill(smem_u32(t0 + 3 * kBwdTile + tok_a * QS + ch8), p.dout + oa * p.C + head * HD + ch8, a_ok);
+    cp_async_16_zfill(smem_u32(t0 + 3 * kBwdTile + tok_b * QS + ch8), p.dout + ob * p.C + head * HD + ch8, b_ok);
+    cp_async_commit();
+  };
+
+  int buf = 0;
+  int ra = 0, rb = 0, ra_n = 0, rb_n = 0;
+  if (static_cast<int>(blockIdx.x) < n_win) {
+    rows_of(blockIdx.x, ra, rb);
+    gather(0, ra, rb);
+  }
+  for (int win = blockIdx.x; win < n_win; win += gridDim.x, buf ^= 1, ra = ra_n, rb = rb_n) {
     const int b = win / nW, wi = win - b * nW;
     const int wy = wi / g.nww, wx = wi - wy * g.nww;
     const bool seam = p.mask == nullptr && g.shift > 0 && (wy == g.nwh - 1 || wx == g.nww - 1);
-    int ra, rb;
-    {
-      int r = wy * g.ws + ay + g.shift, c = wx * g.ws + ax + g.shift;
-      if (r >= g.H) r -= g.H;
-      if (c >= g.W) c -= g.W;
-      ra = (b * g.H + r) * g.W + c;
-      r = wy * g.ws + by + g.shift; c = wx * g.ws + bx + g.shift;
-      if (r >= g.H) r -= g.H;
-      if (c >= g.W) c -= g.W;
-      rb = (b * g.H + r) * g.W + c;
-    }
-    __syncthreads();
+    __nv_bfloat16* const Qs = bwd_smem + buf * 4 * kBwdTile;
+    __nv_bfloat16* const Ks = Qs + kBwdTile;
+    __nv_bfloat16* const Vs = Ks + kBwdTile;
+    __nv_bfloat16* const dOs = Vs + kBwdTile;
+    __syncthreads();   // previous iteration done with the other buffer (dq / dk / dv staging) and with reg_s
     if (seam && threadIdx.x < NP) reg_s[threadIdx.x] = threadIdx.x < g.N ? region_id(g, wy, wx, threadIdx.x) : 0;
-    {
-      const size_t oa = static_cast<size_t>(a_ok ? ra : 0), ob = static_cast<size_t>(b_ok ? rb : 0);
-      const __nv_bfloat16* sa = p.qkv + oa * C3 + head * HD + ch8;
-      const __nv_bfloat16* sb = p.qkv + ob * C3 + head * HD + ch8;
-      cp_async_16_zfill(smem_u32(Qs + tok_a * QS + ch8), sa, a_ok);
-      cp_async_16_zfill(smem_u32(Qs + tok_b * QS + ch8), sb, b_ok);
-      cp_async_16_zfill(smem_u32(Ks + tok_a * QS + ch8), sa + p.C, a_ok);
-      cp_async_16_zfill(smem_u32(Ks + tok_b * QS + ch8), sb + p.C, b_ok);
-      cp_async_16_zfill(smem_u32(Vs + tok_a * QS + ch8), sa + 2 * p.C, a_ok);
-      cp_async_16_zfill(smem_u32(Vs + tok_b * QS + ch8), sb + 2 * p.C, b_ok);
-      cp_async_16_zfill(smem_u32(dOs + tok_a * QS + ch8), p.dout + oa * p.C + head * HD + ch8, a_ok);
-      cp_async_16_zfill(smem_u32(dOs + tok_b * QS + ch8), p.dout + ob * p.C + head * HD + ch8, b_ok);
+    const int next = win + gridDim.x;
+    if (next < n_win) {
+      rows_of(next, ra_n, rb_n);
+      gather(buf ^ 1, ra_n, rb_n);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
-    cp_async_commit();
-    cp_async_wait<0>();
     __syncthreads();
 
     // ---- recompute P = exp(S - lse) --------------------------------------------------------
@@ -615,7 +651,10 @@ int launch_win_attn_bwd(const void* qkv, const void* dout, const float* rpb, con
   int gx = n_win;
   const int cap = (148 * 3 + nH - 1) / nH;  // 3 resident CTAs per SM (register-limited), strided over windows
   if (gx > cap) gx = cap;
-  win_attn_bwd_kernel<<<dim3(gx, nH), 128, 0, stream>>>(p); note_launch();
+  static cudaError_t attr_err = cudaFuncSetAttribute(win_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    kBwdSmemBytes);
+  MTL_CHECK_CUDA(attr_err);
+  win_attn_bwd_kernel<<<dim3(gx, nH), 128, kBwdSmemBytes, stream>>>(p); note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
