@@ -28,6 +28,9 @@ CASES = {
     "s1_fc1_fwd": (100352, 192, 768, 64, [4] * 4, "fc1"),
     "s0_fc2_bwd": (401408, 384, 96, 64, [], "fc2_bwd_single"),
     "s0_proj_bwd": (401408, 96, 96, 64, [], "proj_bwd_single"),
+    "s2_qkv_fwd": (25088, 384, 1152, 64, [], "qkv"),
+    "s2_fc2_fwd": (25088, 1536, 384, 64, [], "fc2_single"),
+    "s2_qkv_bwd": (25088, 384, 1152, 64, [], "qkv_bwd"),
     "s2_fc1_fwd": (25088, 384, 1536, 64, [], "fc1_single"),
     "s2_fc2_bwd": (25088, 1536, 384, 64, [], "fc2_bwd_single"),
     "s3_fc2_bwd": (6272, 3072, 768, 64, [4] * 4, "fc2_bwd"),
@@ -61,8 +64,8 @@ def main():
     if kind in ("fc1", "fc1_single"):
         fn = lambda: ops.linear_fwd(spec, x, wb, bias, a_cat, b_cat, x_tasks_given=xt, act_gelu=True, gelu_grad=True, dropout_p=p, seed=1, save_u=True)
         meta = ("fwd", M, K, N, 1 + (T if xt else 0), S_out, spec.R_pad, sum(spec.ranks), True)
-    elif kind in ("fc2", "proj", "qkv"):
-        res = torch.randn(S_out if kind == "fc2" else 1, M, N, device=dev, generator=g).to(BF) if kind != "qkv" else None
+    elif kind in ("fc2", "proj", "qkv", "fc2_single"):
+        res = torch.randn(S_out if kind.startswith("fc2") else 1, M, N, device=dev, generator=g).to(BF) if kind != "qkv" else None
         ps = torch.ones(S_out, 32, device=dev) if kind != "qkv" else None
         fn = lambda: ops.linear_fwd(spec, x, wb, bias, a_cat, b_cat, x_tasks_given=xt, residual=res, path_scale=ps,
                                     rows_per_sample=M // 32 if ps is not None else 0, dropout_p=p, seed=1, save_u=True)
