@@ -1,7 +1,7 @@
 """Context measurement (not a parity test): the reference algorithm in PyTorch eager on the SAME GPU (the oracle is
 device-agnostic plain torch, i.e. what the reference's nn.Modules execute: F.linear + 2(1+T) skinny matmuls + mul/add
 per MTLoRALinear, roll / window_partition copies, bmm attention, separate LayerNorm / GELU / residual kernels) against
-this repo's fused path, BASELINE config 2 (Swin-T 448, 4 tasks, r 64/4) at a batch that fits both. BASELINE.json's
+this repo's fused path, BASELINE config 2 (Swin-T 448, 4 tasks, r 64/4, batch 32; MTL_SPEED_BATCH overrides). BASELINE.json's
 north_star target is >= 5x at 1 GPU; the measured ratio is printed and written to gpurun_out/eager_vs_fused.json, and
 the test only asserts that the fused path is faster."""
 import contextlib
@@ -38,7 +38,7 @@ def test_fused_beats_eager_reference_algorithm():
         pytest.skip("needs a CUDA device")
     from mtlora_b200 import swin_transformer_mtlora as S
     from mtlora_b200.lora import mark_only_lora_as_trainable
-    B, img = 16, 448
+    B, img = int(os.environ.get("MTL_SPEED_BATCH", "32")), 448   # BASELINE configs[1] batch (README.md:28)
     ranks = [dict({"shared": 64}, **{t: 4 for t in TASKS})] * 4
     ns = types.SimpleNamespace(
         R_PER_TASK_LIST=ranks, SHARED_SCALE=[4.0] * 4, SCALE_PER_TASK_LIST=[{t: 4.0 for t in TASKS}] * 4,
