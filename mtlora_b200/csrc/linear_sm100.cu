@@ -7,13 +7,16 @@
 //   * the rank-space activations U = X.A_cat^T are formed once per tile, converted to a bf16 K-major operand in
 //     shared memory and replayed against B_cat for every output stream ("stream-sequential" delta accumulators);
 //   * the dense accumulator P of a column chunk is shared by all (1+T) stream epilogues;
-//   * two epilogue warp-groups (4 warps each = the 4 TMEM lane quadrants) ping-pong over the items
-//     (chunk, stream): TMEM -> registers -> bias / DropPath scale / GELU / residual -> bf16 -> swizzled smem slab ->
-//     TMA store, so every output element is written exactly once by coalesced bulk stores.
+//   * two epilogue groups of 8 warps (4 TMEM lane quadrants x 2 column halves) ping-pong over the items
+//     (chunk, stream): TMEM -> registers -> bias / DropPath scale / GELU, GELU' / residual -> bf16 -> 64-byte-swizzled
+//     2 KB smem slab -> TMA store, so every output element is written exactly once by coalesced bulk stores;
+//   * one leader warp per group polls the accumulator mbarriers, the others block on a named barrier; the producer
+//     prefetches the epilogue inputs (residual, GELU' factor) of its tile into L2.
 //
-// Warp roles (128 + 128 * kGroups threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4.. = epilogue groups of 4 warps (warp % 4 = TMEM lane quadrant). kGroups = 2: a third group was measured
-// slower (it costs the third store slab, the second accumulator per group and the 128-column chunks).
+// Warp roles (640 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-19 = epilogue
+// (warp % 4 = TMEM lane quadrant); setmaxnreg gives the epilogue warpgroups 104 registers, the control one 64.
+// Planner notes (launch_linear): items of 128 columns wherever TMEM allows (64-column items cost 14-26 % more at any K),
+// except the GELU pair, whose long items need the double-buffered accumulators; a third epilogue group was slower.
 #include "linear_sm100.cuh"
 
 #include <cudaTypedefs.h>

@@ -1,4 +1,6 @@
-// Parameter-gradient reduction C[a, b] += alpha * sum_m rs(m) * P[m, a] * Q[m, b].
+// Parameter-gradient reduction C[a, b] += alpha * sum_m rs(m) * P[m, a] * Q[m, b] — the LEGACY mma.sync path. The hot
+// path is xty_sm100.cu (tcgen05, MN-major operands straight from TMA boxes); this kernel remains for the cases it does
+// not take: alpha != 1, GELU recomputation on load (x_gelu) and operands narrower than 72 columns.
 //
 // This is the only reduction over the (huge) token dimension M in the MTLoRA backward:
 //   dB_s = dY_s^T U_s   (N x r),  dA_s = G_s^T X_s   (r x K),  dW_reduction = dY^T X   (PatchMerging, trainable)
