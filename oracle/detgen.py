@@ -44,7 +44,7 @@ def std_uniform(name, shape, std, mean=0.0):
 def backbone_param_shapes(cfg, ranks, downsampler_lora=False, qkv_bias=True):
     """name -> shape for every parameter of SwinTransformerMTLoRA(num_classes=0), in the reference's
     named_parameters() naming (SURVEY.md §5 checkpoint row; validated against the real model by
-    tools/make_golden.py). `ranks[s]` = {'shared': r_s, task: r_t, ...} = mtlora.R_PER_TASK_LIST[s]."""
+    tests/golden/make_golden.py). `ranks[s]` = {'shared': r_s, task: r_t, ...} = mtlora.R_PER_TASK_LIST[s]."""
     E, ps = cfg.embed_dim, cfg.patch_size
     out = OrderedDict()
     out["patch_embed.proj.weight"] = (E, cfg.in_chans, ps, ps)

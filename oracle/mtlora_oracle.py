@@ -6,7 +6,7 @@ the SwinTransformerMTLoRA stage loop. Only `tests/`, `__graft_entry__.smoke()` a
 `--impl reference` legs may import this module, and only as the checker / the timed CPU baseline — the product
 (`mtlora_b200/`) never imports it and has no CPU fallback.
 
-Parity status: PINNED against the reference itself. `tools/make_golden.py` imports the unmodified reference
+Parity status: PINNED against the reference itself. `tests/golden/make_golden.py` imports the unmodified reference
 modules from /root/reference (with a 3-symbol timm stub), feeds them the deterministic parameters / inputs of
 `oracle/detgen.py`, and stores their outputs and gradients under `tests/golden/`; `tests/test_oracle_golden.py`
 checks this file against those vectors. The reference's own (only) test, kernels/window_process/unit_test.py, is

@@ -1,7 +1,7 @@
 """Generate tests/golden/reference_vectors.npz by running the UNMODIFIED reference (imported from /root/reference)
 on the deterministic inputs of oracle/detgen.py. Run in the build container only (the GPU box has no reference):
 
-    python tools/make_golden.py
+    python tests/golden/make_golden.py
 
 The reference needs `timm.models.layers.{DropPath,to_2tuple,trunc_normal_}` (timm==0.9.2 is not installed here);
 a stub with timm's published semantics is injected before import. Nothing from the reference is copied into the
@@ -14,7 +14,7 @@ import types
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 REF = os.environ.get("MTLORA_REFERENCE", "/root/reference")
 

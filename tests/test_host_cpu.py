@@ -38,7 +38,7 @@ def build(tasks, ranks, **kw):
 @pytest.mark.parametrize("ds", [False, True])
 def test_parameter_surface_matches_reference(ds):
     """Names, order and shapes of named_parameters() == the reference's (validated against the real reference model
-    by tools/make_golden.py through detgen.backbone_param_shapes) — the checkpoint / optimizer-state surface."""
+    by tests/golden/make_golden.py through detgen.backbone_param_shapes) — the checkpoint / optimizer-state surface."""
     cfg = OracleConfig(img_size=224, tasks=("semseg",))
     ranks = [{"shared": 4, "semseg": 4}] * 4
     net = build(["semseg"], ranks, downsampler=ds)

@@ -1,5 +1,5 @@
 """GPU parity of the reference-facing modules (mtlora_b200.swin_transformer_mtlora / mtlora_b200.lora) against
- (a) the golden vectors produced by the UNMODIFIED reference (tests/golden/reference_vectors.npz, tools/make_golden.py)
+ (a) the golden vectors produced by the UNMODIFIED reference (tests/golden/reference_vectors.npz, tests/golden/make_golden.py)
  (b) the CPU oracle evaluated on the same seeded inputs.
 The product computes in bf16 (fp32 accumulation); tolerance = 1e-2 of the tensor's max magnitude for activations and
 input gradients (BASELINE.json north_star, bf16), 2e-2 for parameter gradients that are sums over all tokens.

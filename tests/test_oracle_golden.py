@@ -1,4 +1,4 @@
-"""Pins oracle/mtlora_oracle.py against vectors produced by the unmodified reference (tools/make_golden.py).
+"""Pins oracle/mtlora_oracle.py against vectors produced by the unmodified reference (tests/golden/make_golden.py).
 CPU only. Tolerances are fp32 round-off: both sides run the same math in a different op order."""
 import numpy as np
 import pytest
