@@ -893,6 +893,7 @@ class PatchEmbed(nn.Module):
             f"Input image size ({H}*{W}) doesn't match model ({self.img_size[0]}*{self.img_size[1]})."
         bf16_autocast = x.is_cuda and torch.is_autocast_enabled() and _autocast_cuda_dtype() == BF16
         if (bf16_autocast and type(self.norm) is nn.LayerNorm and x.dtype == torch.float32 and C == 3
+                and not x.requires_grad   # the fused kernel produces no image gradient
                 and tuple(self.patch_size) == (4, 4) and self.embed_dim in (96, 128) and self.proj.bias is not None):
             # one kernel: patch projection + bias + LayerNorm, bf16 tokens out
             return _PatchEmbedFn.apply(x, self.proj.weight, self.proj.bias, self.norm.weight, self.norm.bias,
