@@ -120,6 +120,30 @@ int mtl_linear_bwd_input(const mtl_linear_cfg* cfg, const void* dy, const void* 
                          const void* b_cat_t, void* dx, const void* gelu_aux, const float* path_scale,
                          void* g_save, mtl_stream_t stream);
 
+/* Tiling the planner of the fused linear kernel picks for one launch (test / tuning aid; runs without a GPU).
+ * pass 0 = mtl_linear_fwd (act = MTL_ACT_*, has_residual = a residual is added), pass 1 = mtl_linear_bwd_input
+ * (act != MTL_ACT_NONE = a gelu_aux operand is given). n_sm = size of the persistent grid to balance for.
+ * Returns -1 (mtl_last_error) when the configuration does not fit the kernel's TMEM / shared-memory budget. */
+typedef struct mtl_linear_plan_info {
+  int32_t bn;             /* output columns per chunk */
+  int32_t n_chunks;       /* ceil(N / bn) */
+  int32_t n_splits;       /* work items per 128-row tile */
+  int32_t n_stages;       /* TMA ring depth */
+  int32_t n_slabs;        /* store slabs per epilogue warp */
+  int32_t n_regions;      /* 1 = dense + adapters in one accumulator; else 1 + output streams */
+  int32_t n_pbuf, n_dbuf; /* dense / per-group item accumulators */
+  int32_t d_shared;       /* one delta accumulator shared by both epilogue groups */
+  int32_t tmem_cols;      /* TMEM allocation (power of two <= 512) */
+  int32_t tmem_cols_used;
+  int32_t smem_bytes;     /* dynamic shared memory of the launch (<= 227 KiB) */
+  int32_t n_work;         /* work items walked by the persistent CTAs */
+  int32_t n_groups;       /* rank-space load groups */
+  int32_t s_in, s_out;    /* operand / result streams of the launch */
+  int32_t up_pack;        /* Up tiles per ring stage (1; 2-3 when the packed rank space is wider than 128) */
+} mtl_linear_plan_info;
+int mtl_linear_plan(const mtl_linear_cfg* cfg, int32_t pass, int32_t act, int32_t has_residual, int32_t n_sm,
+                    mtl_linear_plan_info* out);
+
 /* Adapter gradients, accumulated into packed fp32 buffers da_cat [R, K] and db_cat [N, R]:
  *   dB_s += dy[s]^T (ps[s] U_s),   dA_s += G_s^T (ps[s] x_in(s))   (x_in(s): the stream adapter s consumed in forward;
  *   ps = path_scale [1+T, M / rows_per_sample] or NULL)

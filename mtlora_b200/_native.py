@@ -39,6 +39,13 @@ class LinearCfg(ctypes.Structure):
     ]
 
 
+class LinearPlanInfo(ctypes.Structure):
+    """mtl_linear_plan_info: the tiling the planner of the fused linear kernel picks (mtl_linear_plan, no GPU needed)."""
+    _fields_ = [(n, c_int32) for n in (
+        "bn", "n_chunks", "n_splits", "n_stages", "n_slabs", "n_regions", "n_pbuf", "n_dbuf", "d_shared", "tmem_cols",
+        "tmem_cols_used", "smem_bytes", "n_work", "n_groups", "s_in", "s_out", "up_pack")]
+
+
 _CFG_P = ctypes.POINTER(LinearCfg)
 _PP = ctypes.POINTER(c_void_p)
 
@@ -56,6 +63,7 @@ SIGNATURES = {
                                c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "mtl_linear_bwd_input": (c_int, [_CFG_P, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p]),
+    "mtl_linear_plan": (c_int, [_CFG_P, c_int32, c_int32, c_int32, c_int32, ctypes.POINTER(LinearPlanInfo)]),
     "mtl_linear_bwd_params": (c_int, [_CFG_P, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p]),
     "mtl_xty": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_int32, c_float,

@@ -96,6 +96,41 @@ void fill_granules(LinPlan& p, const RankLayout& L, const int* adapter_in) {
     }
 }
 
+// mtl_linear_plan: while `probe` is set on this thread, the linear entry points stop after planning and report the
+// tiling instead of launching (no CUDA call is made, so this works without a device).
+struct PlanProbe {
+  mtl_linear_plan_info* out;
+  int n_sm;
+};
+thread_local PlanProbe* g_probe = nullptr;
+
+int run_linear(LinPlan& p, const void* x, const void* wm, const void* down, const void* up, cudaStream_t stream) {
+  if (g_probe == nullptr) return launch_linear(p, x, wm, down, up, stream);
+  uint32_t smem = 0;
+  if (int e = plan_linear(p, g_probe->n_sm, &smem)) return e;
+  mtl_linear_plan_info* o = g_probe->out;
+  memset(o, 0, sizeof(*o));
+  o->bn = p.BN;
+  o->n_chunks = p.n_chunks;
+  o->n_splits = p.n_splits;
+  o->n_stages = p.n_stages;
+  o->n_slabs = p.n_slabs;
+  o->n_regions = p.n_regions;
+  o->n_pbuf = p.n_pbuf;
+  o->n_dbuf = p.n_dbuf;
+  o->d_shared = p.d_shared;
+  o->tmem_cols = p.tmem_cols;
+  o->tmem_cols_used = p.d_shared ? p.acc_col0 + (p.n_pbuf + 1) * p.BN
+                                 : p.acc_col0 + (p.n_pbuf + 2 * p.n_dbuf) * p.BN;
+  o->smem_bytes = static_cast<int32_t>(smem);
+  o->n_work = p.n_work;
+  o->n_groups = p.n_groups;
+  o->s_in = p.S_in;
+  o->s_out = p.S_out;
+  o->up_pack = p.up_pack;
+  return 0;
+}
+
 int check_ptr16(const void* p, const char* what) {
   MTL_REQUIRE(p != nullptr, "%s is NULL", what);
   MTL_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, "%s must be 16-byte aligned", what);
@@ -236,7 +271,7 @@ int mtl_linear_fwd(const mtl_linear_cfg* cfg, const void* x, const void* w_bf16,
   if (drop && act != MTL_ACT_NONE) p.drop_mode = 1;
   p.drop_p = cfg->dropout_p;
   p.drop_seed = cfg->dropout_seed;
-  return launch_linear(p, x, w_bf16, a_cat, b_cat, S(stream));
+  return run_linear(p, x, w_bf16, a_cat, b_cat, S(stream));
 }
 
 int mtl_linear_bwd_input(const mtl_linear_cfg* cfg, const void* dy, const void* wt_bf16, const void* a_cat_t,
@@ -328,7 +363,27 @@ int mtl_linear_bwd_input(const mtl_linear_cfg* cfg, const void* dy, const void* 
   }
   p.drop_p = cfg->dropout_p;
   p.drop_seed = cfg->dropout_seed;
-  return launch_linear(p, dy, wt_bf16, b_cat_t, a_cat_t, S(stream));
+  return run_linear(p, dy, wt_bf16, b_cat_t, a_cat_t, S(stream));
+}
+
+int mtl_linear_plan(const mtl_linear_cfg* cfg, int32_t pass, int32_t act, int32_t has_residual, int32_t n_sm,
+                    mtl_linear_plan_info* out) {
+  MTL_REQUIRE(cfg != nullptr && out != nullptr, "linear_plan: NULL argument");
+  MTL_REQUIRE(pass == 0 || pass == 1, "linear_plan: pass %d (0 = forward, 1 = input gradient)", pass);
+  MTL_REQUIRE(n_sm > 0, "linear_plan: n_sm=%d", n_sm);
+  // the entry points only validate these pointers (non-NULL, 16-byte aligned) before planning; nothing is dereferenced
+  void* const buf = reinterpret_cast<void*>(uintptr_t{4096});
+  float* const fbuf = reinterpret_cast<float*>(uintptr_t{4096});
+  PlanProbe probe{out, n_sm};
+  g_probe = &probe;
+  int rc;
+  if (pass == 0)
+    rc = mtl_linear_fwd(cfg, buf, buf, fbuf, buf, buf, act, buf, act != MTL_ACT_NONE ? buf : nullptr,
+                        has_residual ? buf : nullptr, 1, nullptr, nullptr, nullptr);
+  else
+    rc = mtl_linear_bwd_input(cfg, buf, buf, buf, buf, buf, act != MTL_ACT_NONE ? buf : nullptr, nullptr, nullptr, nullptr);
+  g_probe = nullptr;
+  return rc;
 }
 
 int mtl_linear_bwd_params(const mtl_linear_cfg* cfg, const void* x, int32_t x_gelu, const void* dy,

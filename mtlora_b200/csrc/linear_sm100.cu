@@ -63,6 +63,12 @@ __host__ __device__ inline SmemLayout smem_layout(int n_stages, int stage_bytes,
   return l;
 }
 
+// Shared-memory address of the i-th Up tile ([BN x 64] bf16, SW128) held by the ring stage starting at `stage_addr`:
+// tile 0 sits in the stage's B half, tiles 1.. in its A half (16 KiB = two 64-row tiles or one 128-row tile).
+__device__ __forceinline__ uint32_t up_tile_addr(uint32_t stage_addr, int i, int bn) {
+  return i == 0 ? stage_addr + kTileABytes : stage_addr + (i - 1) * bn * 128;
+}
+
 __device__ __forceinline__ bool col_in_out(const LinPlan& p, int j, int col) {
   return (col >= p.out_r0[j][0] && col < p.out_r0[j][0] + p.out_len[j][0]) ||
          (col >= p.out_r0[j][1] && col < p.out_r0[j][1] + p.out_len[j][1]);
@@ -386,11 +392,15 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               advance();
             }
           }
-          for (int a = 0; a < n_uatoms; ++a) {
+          // Up tiles of the chunk, up_pack rank atoms per ring stage: the first in the B half, further ones (wide rank
+          // spaces only) in the A half, which these stages do not otherwise use
+          for (int a0 = 0; a0 < n_uatoms; a0 += p.up_pack) {
             mbar_wait(empty_bar(stage), phase ^ 1u, p.wait_hint_ns);
-            const uint32_t b_dst = smem_base + stage * stage_bytes + kTileABytes;
-            mbar_arrive_expect_tx(full_bar(stage), p.BN * 128);
-            tma_load_2d(b_dst, &tm_up, full_bar(stage), a * 64, c * p.BN);
+            const int na = n_uatoms - a0 < p.up_pack ? n_uatoms - a0 : p.up_pack;
+            mbar_arrive_expect_tx(full_bar(stage), na * p.BN * 128);
+            for (int i = 0; i < na; ++i)
+              tma_load_2d(up_tile_addr(smem_base + stage * stage_bytes, i, p.BN), &tm_up, full_bar(stage), (a0 + i) * 64,
+                          c * p.BN);
             advance();
           }
         }
@@ -479,14 +489,15 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               mbar_wait(u_ready, lw & 1u, p.wait_hint_ns);
               u_waited = true;
             }
-            // the B_cat tiles of all rank atoms of this chunk occupy n_uatoms consecutive ring stages
-            int st[kMaxUAtoms];
+            // the Up tiles of all rank atoms of this chunk occupy n_up_stages consecutive ring stages
+            uint32_t up_addr[kMaxUAtoms];
             {
               int s = stage;
               uint32_t ph = phase;
-              for (int a = 0; a < n_uatoms; ++a) {
+              for (int a0 = 0; a0 < n_uatoms; a0 += p.up_pack) {
                 mbar_wait(full_bar(s), ph, p.wait_hint_ns);
-                st[a] = s;
+                for (int i = 0; i < p.up_pack && a0 + i < n_uatoms; ++i)
+                  up_addr[a0 + i] = up_tile_addr(smem_base + s * stage_bytes, i, p.BN);
                 if (++s == p.n_stages) {
                   s = 0;
                   ph ^= 1u;
@@ -522,7 +533,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               }
               for (int a = 0; a < n_uatoms; ++a) {
                 const uint64_t adesc = umma_desc_sw128(usm_base + a * kTileABytes);
-                const uint64_t bdesc = umma_desc_sw128(smem_base + st[a] * stage_bytes + kTileABytes);
+                const uint64_t bdesc = umma_desc_sw128(up_addr[a]);
                 for (int q = 0; q < 4; ++q) {
                   const int col = a * 64 + q * 16;
                   if (col >= p.R_pad) break;
@@ -536,7 +547,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 ++G;
               }
             }
-            for (int a = 0; a < n_uatoms; ++a) {
+            for (int a0 = 0; a0 < n_uatoms; a0 += p.up_pack) {
               umma_commit(empty_bar(stage));
               advance();
             }
@@ -921,8 +932,7 @@ namespace {
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 }  // namespace
 
-int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, const void* up,
-                  cudaStream_t stream) {
+int plan_linear(LinPlan& p, int n_sm, uint32_t* smem_bytes_out) {
   MTL_REQUIRE(p.M > 0 && p.Kc > 0 && p.Nn > 0, "linear: empty problem (M=%d K=%d N=%d)", p.M, p.Kc, p.Nn);
   MTL_REQUIRE(p.Kc % 16 == 0 && p.Nn % 16 == 0, "linear: K (%d) and N (%d) must be multiples of 16", p.Kc, p.Nn);
   MTL_REQUIRE(p.R_pad % 16 == 0 && p.R_pad <= 16 * LIN_MAX_GRAN, "linear: rank space %d unsupported (<= %d)",
@@ -945,7 +955,7 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
   auto cols = [&](int bn_, int pb, int db) { return u_cols + (pb + kGroups * db) * bn_; };
   const int n_uatoms = (p.R_pad + 63) / 64;
   MTL_REQUIRE(n_uatoms <= kMaxUAtoms, "linear: too many rank atoms");
-  const int min_stages = n_uatoms > 0 ? n_uatoms + 2 : 2;
+  int min_stages = n_uatoms > 0 ? n_uatoms + 2 : 2;   // the Up tiles of a chunk are resident together, + 2 to stream
   // epilogues with two outputs per half (GELU pair) or with TMA-staged inputs want a third store slab per warp:
   // with two, every half waits for the bulk store that just left (measured: 12.7 us instead of ~5 us per item)
   const bool ep_dual = p.ep_mode == LIN_EP_GELU_DUAL || p.ep_mode == LIN_EP_GELU_DUAL_GRAD;
@@ -1029,12 +1039,19 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
   }
   p.stage_b_bytes = bn * 128;
   const int stage_bytes = kTileABytes + p.stage_b_bytes;
+  // Wide rank spaces (R_pad > 128: the U operand alone takes 48-80 KiB): one Up tile per stage no longer fits next
+  // to the store slabs. Pack the tiles — the A half of those stages is free — and, if still short, stream with one
+  // spare stage instead of two.
+  p.up_pack = 1;
+  if (n_uatoms > 0 && smem_layout(min_stages, stage_bytes, p.R_pad, 2).total + 1024 > 227u * 1024) {
+    p.up_pack = 1 + kTileABytes / (bn * 128);
+    const int up_stages = (n_uatoms + p.up_pack - 1) / p.up_pack;
+    min_stages = up_stages + 2;
+    if (smem_layout(min_stages, stage_bytes, p.R_pad, 2).total + 1024 > 227u * 1024) min_stages = up_stages + 1;
+  }
 
   // ---- work decomposition: (128-row tile, column split), persistent CTAs ---------------------------------------
   const int m_tiles = (p.M + LIN_BM - 1) / LIN_BM;
-  int dev = 0, n_sm = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   // Column splits: with few row tiles, split the chunks of a tile over several work items so that the persistent
   // grid is balanced (every split repeats the rank-space phase, modelled as one extra 64-column chunk).
   p.n_splits = 1;
@@ -1069,6 +1086,21 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
     --p.n_stages;
   const uint32_t smem_bytes = smem_layout(p.n_stages, stage_bytes, p.R_pad, p.n_slabs).total + 1024;
   MTL_REQUIRE(smem_bytes <= 227 * 1024, "linear: shared memory %u exceeds 227 KiB", smem_bytes);
+  MTL_REQUIRE(p.ep_mode >= 0 && p.ep_mode <= 4, "linear: unknown epilogue mode %d", p.ep_mode);
+  MTL_REQUIRE(!((ep_aux || ep_dual) && p.res != nullptr), "linear: GELU epilogues cannot take a residual");
+  *smem_bytes_out = smem_bytes;
+  return 0;
+}
+
+int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, const void* up,
+                  cudaStream_t stream) {
+  int dev = 0, n_sm = 148;
+  MTL_CHECK_CUDA(cudaGetDevice(&dev));
+  MTL_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  uint32_t smem_bytes = 0;
+  if (int e = plan_linear(p, n_sm, &smem_bytes)) return e;
+  const bool ep_dual = p.ep_mode == LIN_EP_GELU_DUAL || p.ep_mode == LIN_EP_GELU_DUAL_GRAD;
+  const bool ep_aux = p.ep_mode == LIN_EP_GELU_BWD || p.ep_mode == LIN_EP_MUL_AUX;
 
   // ---- tensor maps ---------------------------------------------------------------------------
   CUtensorMap tm_x, tm_w, tm_down, tm_up, tm_y, tm_y2, tm_u, tm_in, tm_pf;
@@ -1095,7 +1127,6 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
   } else {
     tm_u = tm_y;
   }
-  MTL_REQUIRE(!((ep_aux || ep_dual) && p.res != nullptr), "linear: GELU epilogues cannot take a residual");
   // tm_pf: the same tensor with [128 rows x 64 columns] boxes, used by the producer to prefetch the epilogue inputs
   // of a work item into L2 while its accumulators are still being formed
   if (ep_aux) {
@@ -1146,7 +1177,6 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
     MTL_CHECK_CUDA(cudaMalloc(&p.trace, 4 * 2048 * sizeof(unsigned long long)));
     MTL_CHECK_CUDA(cudaMemsetAsync(p.trace, 0, 4 * 2048 * sizeof(unsigned long long), stream));
   }
-  MTL_REQUIRE(p.ep_mode >= 0 && p.ep_mode <= 4, "linear: unknown epilogue mode %d", p.ep_mode);
 
   int grid = p.n_work < n_sm ? p.n_work : n_sm;
   if (max_ctas == 0) grid = p.n_work;

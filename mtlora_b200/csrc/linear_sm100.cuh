@@ -43,6 +43,7 @@ struct LinPlan {
   int d_shared;   // multi mode, one output stream: a single delta accumulator shared by both epilogue groups
   int n_work;     // work items = row tiles x column splits (walked by persistent CTAs)
   int n_slabs;    // per-epilogue-warp store slabs in shared memory
+  int up_pack;    // Up tiles ([BN x 64] per rank atom) per ring stage: 1, or 2-3 when the rank space is wide
   int acc_col0;   // first accumulator column in TMEM
   int tmem_cols;  // allocation size (power of two >= 32)
 
@@ -90,7 +91,12 @@ struct LinPlan {
 int make_tmap(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
               CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, uint64_t pitch = 0);
 
-// Host side: fills the derived tiling fields of `plan`, encodes tensor maps, launches.
+// Host side, no CUDA calls: validates `plan` and fills its derived tiling fields (chunk width, TMEM / shared-memory
+// budget, column splits for a grid of `n_sm` persistent CTAs). Returns 0 and the dynamic shared-memory size, or -1
+// with mtl_last_error() set when the problem does not fit the kernel.
+int plan_linear(LinPlan& plan, int n_sm, uint32_t* smem_bytes);
+
+// Host side: plan_linear for the current device, tensor maps, launch.
 // x: [S_in, M, Kc], wm: [Nn, Kc], down: [R_pad, Kc], up: [Nn, R_pad]; all bf16 row-major.
 int launch_linear(LinPlan plan, const void* x, const void* wm, const void* down, const void* up,
                   cudaStream_t stream);

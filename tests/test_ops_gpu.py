@@ -105,6 +105,13 @@ LINEAR_CASES = [
     ("equal_r",   520,   96,   384, 32,  [32, 32],     True,  False, 0,    False),
     ("big",       50176, 96,   384, 64,  [4, 4, 4, 4], True,  True,  0,    False),
     ("one_task",  128,   96,   96,  4,   [4],          False, False, 1,    False),
+    # packed rank space wider than 128 columns (BASELINE.json configs[4]: rank sweep up to r = 128; equal ranks of 64):
+    # the Up tiles of a chunk share ring stages (LinPlan::up_pack), checked on CPU by tests/test_planner_cpu.py
+    ("wide_r128", 392,   96,   288, 128, [4, 4, 4, 4], True,  False, 0,    False),
+    ("wide_noxt", 300,   384,  96,  128, [16] * 4,     False, False, 1,    False),
+    ("wide_proj", 392,   96,   96,  64,  [64] * 4,     True,  False, 1,    True),
+    ("wide_fc1",  40000, 96,   384, 64,  [64] * 4,     True,  True,  0,    False),
+    ("wide_fc2",  3136,  1536, 384, 64,  [64] * 4,     True,  False, 5,    False),
 ]
 
 
@@ -328,7 +335,7 @@ def test_linear_dropout_stream(ops):
     check(db[:, 16:20], pr["lora_tasks_B.t0"].grad, tol=2e-2, what="dB task0")
 
 
-@pytest.mark.parametrize("r_s", [4, 64])
+@pytest.mark.parametrize("r_s", [4, 64, 256])
 def test_linear_bwd_input_dropout_long_contraction(ops, r_s):
     """Single-stream input gradient with LoRA dropout and a long contraction (stage-2/3 layers): dense accumulator
     double-buffered + ONE delta accumulator shared by the two epilogue groups, 128-column chunks, several work items
