@@ -15,7 +15,7 @@
 //
 // Warp roles (640 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-19 = epilogue
 // (warp % 4 = TMEM lane quadrant); setmaxnreg gives the epilogue warpgroups 104 registers, the control one 64.
-// Planner notes (launch_linear): items of 128 columns wherever TMEM allows (64-column items cost 14-26 % more at any K),
+// Planner notes (plan_linear): items of 128 columns wherever TMEM allows (64-column items cost 14-26 % more at any K),
 // except the GELU pair, whose long items need the double-buffered accumulators; a third epilogue group was slower.
 #include "linear_sm100.cuh"
 
@@ -47,8 +47,8 @@ constexpr int kMaxStages = 8;
 constexpr int kMaxUAtoms = LIN_MAX_GRAN / 4;
 
 struct SmemLayout {
-  uint32_t usm;    // n_uatoms * 16 KiB
-  uint32_t slabs;  // 8 warps * n_slabs * 4 KiB
+  uint32_t usm;    // U operand: n_uatoms * 16 KiB, after the ring stages
+  uint32_t slabs;  // kEpiWarps * n_slabs * kSlabBytes
   uint32_t bars;
   uint32_t total;
 };
