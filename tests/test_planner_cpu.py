@@ -72,7 +72,7 @@ def test_every_backbone_layer_gets_a_plan(nat, embed):
             if not rt and xt:
                 continue
             what = f"{name} embed={embed} r={rs}/{rt} xt={xt} drop={drop}"
-            # forward (fc1 keeps the GELU pair only without dropout on the activation stream: drop_mode 1 adds a stream)
+            # forward: operand streams = x, the T task inputs when given, and D(x) when LoRA dropout is on
             rc, o, err = plan(nat, K, Nf, M, rs, rt, xt, 0, act, res, drop)
             assert rc == 0, f"{what} fwd: {err}"
             check_info(o, K, Nf, M, what + " fwd")
