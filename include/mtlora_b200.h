@@ -228,6 +228,43 @@ int mtl_add(const void* a, const void* b, void* out, int64_t n, mtl_stream_t str
  * (shortcut + drop_path(stream), swin_transformer_mtlora.py:389-392). */
 int mtl_sum_streams(const void* x, const void* extra, void* out, int32_t S, int64_t n, mtl_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Optimizer step over the trainable tensors of the path — main.py:341-353 -> utils.py:348-369
+ * (NativeScalerWithGradNormCount: scaler.unscale_ + clip_grad_norm_ + scaler.step(AdamW), optimizer.py:58-60)
+ *
+ * The trainable tensors (~200 adapters, LayerNorm affines, rel-pos tables, reductions) are described ONCE by a
+ * device-side segment table; a step is two launches whatever their number. `segs[i].offset` addresses the two flat
+ * fp32 moment buffers; `prefix[i]` = number of MTL_OPT_CHUNK-element chunks before segment i (prefix[n_segs] =
+ * n_chunks), both in device memory. A segment whose `grad` is NULL (grad is None) is skipped entirely, like
+ * torch.optim skips parameters without a gradient.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define MTL_OPT_CHUNK 4096
+#define MTL_OPT_MAX_GROUPS 8
+typedef struct mtl_opt_seg {
+  float* param;      /* fp32 master parameter (updated in place) */
+  const float* grad; /* fp32 gradient, same shape, contiguous; NULL = no gradient this step */
+  int64_t offset;    /* element offset of this tensor's moments in flat_m / flat_v */
+  int64_t numel;
+  int32_t group;     /* index into the groups array of mtl_opt_adamw */
+  int32_t pad_;
+} mtl_opt_seg;
+typedef struct mtl_opt_group {
+  float lr, beta1, beta2, eps, weight_decay;
+} mtl_opt_group;
+int mtl_opt_seg_size(void);
+/* out_sq[0] = sum of squares of every gradient in the table (inf / nan propagate). */
+int mtl_opt_sqnorm(const mtl_opt_seg* segs, const int32_t* prefix, int32_t n_segs, int32_t n_chunks, float* out_sq,
+                   mtl_stream_t stream);
+/* One AdamW (adam_w = 1) / Adam-with-L2 (adam_w = 0) step. state: device float[4] = {steps taken, scratch, total grad
+ * norm of this step (when sqnorm given), unused}, zero-initialised by the caller and owned by the optimizer.
+ * grad_scale / found_inf: the GradScaler's device scalars or NULL (torch.amp contract of fused optimizers: gradients
+ * are divided by *grad_scale, the whole step — including the step counter — is skipped when *found_inf != 0).
+ * sqnorm: result of mtl_opt_sqnorm on the same (still scaled) gradients, needed when max_norm > 0:
+ * coef = min(1, max_norm / (sqrt(sqnorm) / grad_scale + 1e-6)) (torch.nn.utils.clip_grad_norm_). */
+int mtl_opt_adamw(const mtl_opt_seg* segs, const int32_t* prefix, int32_t n_segs, int32_t n_chunks, float* flat_m,
+                  float* flat_v, float* state, const mtl_opt_group* groups, int32_t n_groups, const float* grad_scale,
+                  const float* found_inf, const float* sqnorm, float max_norm, int32_t adam_w, mtl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,18 @@ class LinearPlanInfo(ctypes.Structure):
         "tmem_cols_used", "smem_bytes", "n_work", "n_groups", "s_in", "s_out", "up_pack")]
 
 
+class OptSeg(ctypes.Structure):
+    """mtl_opt_seg: one trainable tensor of the flat optimizer step."""
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("offset", c_int64), ("numel", c_int64), ("group", c_int32),
+                ("pad_", c_int32)]
+
+
+class OptGroup(ctypes.Structure):
+    """mtl_opt_group: hyper-parameters of one torch param_group."""
+    _fields_ = [("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("weight_decay", c_float)]
+
+
+MTL_OPT_CHUNK, MTL_OPT_MAX_GROUPS = 4096, 8
 _CFG_P = ctypes.POINTER(LinearCfg)
 _PP = ctypes.POINTER(c_void_p)
 
@@ -88,6 +100,10 @@ SIGNATURES = {
     "mtl_patch_embed_fwd": (c_int, [c_void_p] * 10 + [c_int32] * 4 + [c_float, c_void_p]),
     "mtl_scale_rows_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int32, c_void_p]),
     "mtl_sum_streams": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p]),
+    "mtl_opt_seg_size": (c_int, []),
+    "mtl_opt_sqnorm": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "mtl_opt_adamw": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                              ctypes.POINTER(OptGroup), c_int32, c_void_p, c_void_p, c_void_p, c_float, c_int32, c_void_p]),
 }
 
 _lib = None

@@ -586,4 +586,21 @@ int mtl_sum_streams(const void* x, const void* extra, void* out, int32_t Sn, int
   return launch_sum_streams(x, extra, out, Sn, n, S(stream));
 }
 
+int mtl_opt_seg_size(void) { return static_cast<int>(sizeof(mtl_opt_seg)); }
+
+int mtl_opt_sqnorm(const mtl_opt_seg* segs, const int32_t* prefix, int32_t n_segs, int32_t n_chunks, float* out_sq,
+                   mtl_stream_t stream) {
+  MTL_REQUIRE(segs != nullptr && prefix != nullptr, "mtl_opt_sqnorm: NULL table");
+  return opt_sqnorm(segs, prefix, n_segs, n_chunks, out_sq, S(stream));
+}
+
+int mtl_opt_adamw(const mtl_opt_seg* segs, const int32_t* prefix, int32_t n_segs, int32_t n_chunks, float* flat_m,
+                  float* flat_v, float* state, const mtl_opt_group* groups, int32_t n_groups, const float* grad_scale,
+                  const float* found_inf, const float* sqnorm, float max_norm, int32_t adam_w, mtl_stream_t stream) {
+  MTL_REQUIRE(segs != nullptr && prefix != nullptr && flat_m != nullptr && flat_v != nullptr && state != nullptr &&
+                  groups != nullptr, "mtl_opt_adamw: NULL argument");
+  return opt_adamw(segs, prefix, n_segs, n_chunks, flat_m, flat_v, state, groups, n_groups, grad_scale, found_inf,
+                   sqnorm, max_norm, adam_w, S(stream));
+}
+
 }  // extern "C"

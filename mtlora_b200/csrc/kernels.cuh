@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/mtlora_b200.h"
+
 namespace mtl {
 
 // attention.cu ------------------------------------------------------------------------------------
@@ -79,5 +81,12 @@ struct XtyJobGroup {
 };
 int launch_xty_groups(const XtyOperand* wide, const XtyOperand* rank, const XtyJobGroup* groups, int n_groups,
                       long M, int rows_per_sample, cudaStream_t stream);
+
+// optim.cu ----------------------------------------------------------------------------------------
+int opt_sqnorm(const mtl_opt_seg* segs, const int32_t* prefix, int n_segs, int n_chunks, float* out,
+               cudaStream_t stream);
+int opt_adamw(const mtl_opt_seg* segs, const int32_t* prefix, int n_segs, int n_chunks, float* flat_m, float* flat_v,
+              float* state, const mtl_opt_group* groups, int n_groups, const float* grad_scale, const float* found_inf,
+              const float* sqnorm, float max_norm, int adam_w, cudaStream_t stream);
 
 }  // namespace mtl

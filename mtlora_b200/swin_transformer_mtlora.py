@@ -985,7 +985,21 @@ class SwinTransformerMTLoRA(nn.Module):
     def no_weight_decay_keywords(self):
         return {'relative_position_bias_table'}
 
+    def _attach_grad_sync(self):
+        """Data-parallel runs (torch.distributed initialised, world size > 1): average the trainable gradients of the
+        backbone over the ranks from autograd hooks, so `main.py`'s loop needs no change (mtlora_b200/dist.py). Cheap
+        to call every forward: parameters already covered are skipped."""
+        from . import dist as _dist
+        if not (torch.distributed.is_available() and torch.distributed.is_initialized()) or \
+                torch.distributed.get_world_size() == 1 or not _dist.auto_sync_enabled():
+            return
+        gs = _dist.sync_gradients(self)
+        if gs is not None:
+            self.__dict__.setdefault("_grad_syncs", []).append(gs)
+
     def forward_features(self, x, return_stages=False, flatten_ft=False):
+        if self.training and torch.is_grad_enabled():
+            self._attach_grad_sync()
         x = self.patch_embed(x)
         if self.ape:
             x = x + self.absolute_pos_embed

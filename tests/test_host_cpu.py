@@ -190,3 +190,119 @@ def test_bench_reference_arm_prints_contract_line():
               "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in line, k
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["cores"] >= 1
+
+
+def _gradsync_worker(rank, world, port, out):
+    """An UNMODIFIED training loop (forward, loss.backward(), optimizer.step()) on two ranks: gradients arrive averaged
+    in p.grad without any call into the reducer (mtlora_b200/dist.py, hook-driven)."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mtlora_b200.dist import GradSync, sync_gradients
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 4), torch.nn.Tanh(),
+                              torch.nn.Linear(4, 3))
+    unused = torch.nn.Parameter(torch.ones(3))      # never reached by backward on any rank (quirk 8)
+    net.register_parameter("unused", unused)
+    net[2].bias.requires_grad_(False)
+    ref = [p.detach().clone() for p in net.parameters()]
+    gs = sync_gradients(net, n_buckets=3)
+    assert isinstance(gs, GradSync) and len(gs.buckets) == 3 and sync_gradients(net) is None   # covered only once
+    ok = True
+    for it in range(3):
+        xs = [torch.randn(7, 6, generator=torch.Generator().manual_seed(100 * it + r)) for r in range(world)]
+        loss = net(xs[rank]).pow(2).mean()
+        net.zero_grad(set_to_none=True)
+        loss.backward()                               # <- nothing else: the hooks do the exchange
+        # expected: mean over ranks of the per-rank gradients, computed locally on a copy
+        exp = None
+        for r in range(world):
+            import copy
+            m2 = copy.deepcopy(net)
+            for p in m2.parameters():
+                p.grad = None
+            m2(xs[r]).pow(2).mean().backward()
+            g = [None if p.grad is None else p.grad.clone() for p in m2.parameters()]
+            exp = g if exp is None else [None if a is None else a + b for a, b in zip(exp, g)]
+        for p, e in zip(net.parameters(), exp):
+            if e is None:
+                ok = ok and p.grad is None
+            else:
+                ok = ok and p.grad is not None and torch.allclose(p.grad, e / world, atol=1e-6)
+    ok = ok and gs.n_reductions == 9 and unused.grad is None
+    del ref
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_grad_sync_hooks_gloo_world2():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_gradsync_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}
+
+
+def _gradsync_asym_worker(rank, world, port, out, exact):
+    """Asymmetric None gradients: rank 1 never produces a gradient for `b`. exact_presence=True hands rank 1 the
+    average; the default detects the disagreement (one step late) and raises instead of letting the replicas diverge."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mtlora_b200.dist import GradSync
+    a = torch.nn.Parameter(torch.ones(4))
+    b = torch.nn.Parameter(torch.ones(3))
+    gs = GradSync([a, b], n_buckets=1, exact_presence=exact)
+    res = "ok"
+    try:
+        for it in range(2):
+            a.grad = b.grad = None
+            loss = (a * (rank + 1)).sum()
+            if rank == 0:
+                loss = loss + (b * 2.0).sum()
+            loss.backward()
+            if exact:
+                good = torch.allclose(a.grad, torch.full((4,), 1.5)) and b.grad is not None and \
+                    torch.allclose(b.grad, torch.full((3,), 1.0))      # (2 + 0) / 2
+                res = res if good else "wrong values"
+    except RuntimeError as e:
+        res = "raised" if "disagree" in str(e) else f"other error: {e}"
+    out[rank] = res
+    del gs
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_grad_sync_asymmetric_none_gloo_world2(exact):
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_gradsync_asym_worker, args=(world, _free_port(), out, exact), nprocs=world, join=True)
+    assert dict(out) == ({0: "ok", 1: "ok"} if exact else {0: "raised", 1: "raised"})
+
+
+def _reducer_asym_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mtlora_b200.dist import AdapterGradReducer
+    a, b = torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(3))
+    a.grad = torch.full((4,), float(rank + 1))
+    if rank == 0:
+        b.grad = torch.full((3,), 6.0)
+    AdapterGradReducer([a, b]).reduce()
+    out[rank] = bool(torch.allclose(a.grad, torch.full((4,), 1.5)) and b.grad is not None
+                     and torch.allclose(b.grad, torch.full((3,), 3.0)))
+    dist.destroy_process_group()
+
+
+def test_adapter_grad_reducer_asymmetric_none_gloo_world2():
+    """a parameter that is None on one rank only must still receive the averaged gradient there."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_reducer_asym_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}
