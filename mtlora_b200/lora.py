@@ -47,6 +47,16 @@ class LinearEngine:
         self.linear = linear
         self.spec = spec
         self.tasks = list(tasks) if tasks else []
+        # shared_mode 'addition' (lora.py:275-282): no shared adapter; the kernels run with an all-zero rank-1 stand-in
+        # so that stream 0 carries the frozen product, the LayerNorm-of-the-task-sum tail is `_AdditionTailFn`
+        self.addition = owner is not None and getattr(owner, "shared_mode", "") == "addition" and spec.r_shared > 0
+        self._zero = None
+        self.invalidate()
+
+    def invalidate(self):
+        """Drop the staged bf16 operand copies (frozen W / W^T, packed adapters). They are keyed on (data_ptr, _version)
+        of the fp32 masters, which in-place ops through `.data` (`p.data.copy_()`, weight surgery, EMA scripts) do NOT
+        bump: call this after such writes (load_state_dict / optimizer steps — torch.optim or FlatAdamW — need nothing)."""
         self._wkey = None
         self._w = self._wt = None
         self._akey = None
@@ -57,7 +67,13 @@ class LinearEngine:
         o = self.owner
         if self.spec.r_shared == 0:
             return []
-        ps = [o.lora_shared_A, o.lora_shared_B]
+        if self.addition:
+            w = self.linear.weight
+            if self._zero is None or self._zero[0].device != w.device:
+                self._zero = (torch.zeros((1, self.spec.K), device=w.device), torch.zeros((self.spec.Nf, 1), device=w.device))
+            ps = [self._zero[0], self._zero[1]]
+        else:
+            ps = [o.lora_shared_A, o.lora_shared_B]
         ps += [o.lora_tasks_A[t] for t in self.tasks] + [o.lora_tasks_B[t] for t in self.tasks]
         return ps
 
@@ -67,7 +83,7 @@ class LinearEngine:
         if o is None or self.spec.r_shared == 0:
             return []
         out = []
-        if isinstance(getattr(o, "lora_shared_scale", None), nn.Parameter):
+        if isinstance(getattr(o, "lora_shared_scale", None), nn.Parameter) and not self.addition:
             out.append((0, o.lora_shared_scale))
         ts = getattr(o, "lora_task_scale", None)
         if isinstance(ts, nn.ParameterDict):
@@ -77,8 +93,8 @@ class LinearEngine:
     def params(self):
         """Parameters in the order `backward` reports gradients: weight, bias?, shared A, B, task A..., task B..., scales."""
         lin = self.linear
-        return ([lin.weight] + ([lin.bias] if lin.bias is not None else []) + self.adapters()
-                + [p for _, p in self.scales()])
+        return ([lin.weight] + ([lin.bias] if lin.bias is not None else [])
+                + [p for p in self.adapters() if isinstance(p, nn.Parameter)] + [p for _, p in self.scales()])
 
     def stage(self):
         w = self.linear.weight
@@ -194,18 +210,24 @@ class _LinearFn(torch.autograd.Function):
         ctx.engine = engine
         need = any(ctx.needs_input_grad[4:])
         y, _, saved = engine.forward(x, xt=xt, dropout_p=dropout_p, seed=seed, save=need)
-        ctx.saved = saved
+        if need:
+            tens = {k: v for k, v in saved.items() if torch.is_tensor(v)}
+            ctx.meta = {k: v for k, v in saved.items() if not torch.is_tensor(v)}
+            ctx.keys = list(tens)
+            ctx.save_for_backward(*tens.values())
         ctx.params = params
         return y
 
     @staticmethod
     def backward(ctx, dy):
         eng = ctx.engine
-        dx, grads = eng.backward(ctx.saved, dy.contiguous())
-        if ctx.saved["dropout_p"] > 0 and eng.spec.r_shared > 0:
+        saved = dict(ctx.meta)
+        saved.update(zip(ctx.keys, ctx.saved_tensors))
+        dx, grads = eng.backward(saved, dy.contiguous())
+        if saved["dropout_p"] > 0 and eng.spec.r_shared > 0:
             # the appended D(x[0]) stream is produced from x[0] inside the wrapper; its gradient is folded into dx[0]
             pad = torch.zeros_like(dx[:1])
-            dx = torch.cat([dx, pad]) if dx.shape[0] + 1 == ctx.saved["x"].shape[0] else dx
+            dx = torch.cat([dx, pad]) if dx.shape[0] + 1 == saved["x"].shape[0] else dx
         return (None, None, None, None, dx) + tuple(grads.get(p) for p in ctx.params)
 
 
@@ -230,9 +252,36 @@ def run_linear_standalone(engine, x, x_tasks, dropout_p, training):
     xs = torch.stack(streams)
     y = _LinearFn.apply(engine, xt, p, seed, xs, *engine.params())
     outs = [y[i].reshape(*lead, spec.Nf).to(in_dtype) for i in range(spec.S_out)]
+    if engine.addition:
+        ln = engine.owner.lora_norm
+        outs[0] = _AdditionTailFn.apply(y, ln.weight, ln.bias, ln.eps).reshape(*lead, spec.Nf).to(in_dtype)
     if spec.S_out == 1 and not (spec.r_shared > 0 and engine.tasks):
         return outs[0], None
     return outs[0], {t: outs[1 + i] for i, t in enumerate(engine.tasks)}
+
+
+class _AdditionTailFn(torch.autograd.Function):
+    """shared_mode 'addition' (reference lora.py:279-282): y[0] + LayerNorm(sum_t y[1 + t]) over the stream-stacked output
+    of the linear kernel (y[0] = frozen product, y[1 + t] = task outputs), through mtl_sum_streams / mtl_layernorm_* /
+    mtl_add."""
+
+    @staticmethod
+    def forward(ctx, y, weight, bias, eps):
+        w, b = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        tot = ops.sum_streams(y[1:].contiguous())
+        ln, mean, rstd = ops.layernorm_fwd(tot, w, b, eps)
+        ctx.save_for_backward(tot, w, mean, rstd)
+        ctx.n_tasks = y.shape[0] - 1
+        ctx.want = weight.requires_grad or bias.requires_grad
+        return ops.add(y[0].contiguous(), ln)
+
+    @staticmethod
+    def backward(ctx, dout):
+        tot, w, mean, rstd = ctx.saved_tensors
+        d = dout if (dout.dtype == BF16 and dout.is_contiguous()) else dout.to(BF16).contiguous()
+        dtot, dw, db = ops.layernorm_bwd(d, tot, w, mean, rstd, want_param_grads=ctx.want)
+        dy = torch.cat([d.unsqueeze(0), dtot.unsqueeze(0).expand(ctx.n_tasks, *dtot.shape)])
+        return dy, dw, db, None
 
 
 class _DropoutFn(torch.autograd.Function):
@@ -266,10 +315,6 @@ class MTLoRALinear(LoRALayer):
         has_tasks = tasks is not None
         if not has_tasks and shared_mode not in ["matrix"]:
             shared_mode = "matrix"
-        if shared_mode not in ("matrix", "matrixv2"):
-            raise NotImplementedError(
-                f"mtlora_b200: shared_mode={shared_mode!r} is not implemented yet ('matrix' — every shipped YAML — and "
-                "'matrixv2' are)")
         if isinstance(r, int):
             r = {"shared": r}
         super().__init__(r=r["shared"], lora_alpha=lora_shared_scale, lora_dropout=lora_dropout)
@@ -293,21 +338,23 @@ class MTLoRALinear(LoRALayer):
                     self.lora_task_scale = {task: lora_task_scale[task] for task in tasks}
                     s_tasks = [float(self.lora_task_scale[t]) for t in tasks]
                 r_tasks = [r[t] for t in tasks]
-            self.lora_shared_A = nn.Parameter(self.linear.weight.new_zeros((r["shared"], in_features)))
-            self.lora_shared_B = nn.Parameter(self.linear.weight.new_zeros((out_features, r["shared"])))
+            if shared_mode == "addition":
+                assert has_tasks
+                self.lora_norm = nn.LayerNorm(out_features)          # reference :217-219
+            else:
+                self.lora_shared_A = nn.Parameter(self.linear.weight.new_zeros((r["shared"], in_features)))
+                self.lora_shared_B = nn.Parameter(self.linear.weight.new_zeros((out_features, r["shared"])))
             if trainable_scale_shared:
                 self.lora_shared_scale = nn.Parameter(torch.FloatTensor([float(lora_shared_scale)]))   # reference :229-231
             else:
                 self.lora_shared_scale = lora_shared_scale
             self.reset_parameters()
-        spec = ops.LinearSpec(in_features, out_features, r["shared"], r_tasks,
+        addition = shared_mode == "addition" and r["shared"] > 0
+        spec = ops.LinearSpec(in_features, out_features, 1 if addition else r["shared"], r_tasks,
                               1.0 if (trainable_scale_shared and r["shared"] > 0) else float(lora_shared_scale), s_tasks,
-                              shared_mode=shared_mode if r_tasks else "matrix")
+                              shared_mode=shared_mode if (r_tasks and not addition) else "matrix")
         self._engine = LinearEngine(self, self.linear, spec, tasks if (has_tasks and r["shared"] > 0) else None)
-
-    @property
-    def engine(self):
-        return self._engine
+        self._plain_engine = None
 
     def reset_parameters(self):
         """A ~ kaiming_uniform(a=sqrt(5)), B = 0 (reference :236-247): the layer starts equal to the frozen linear."""
@@ -319,11 +366,51 @@ class MTLoRALinear(LoRALayer):
                 nn.init.kaiming_uniform_(self.lora_tasks_A[task], a=math.sqrt(5))
                 nn.init.zeros_(self.lora_tasks_B[task])
 
+    # ---- inference merge (the reference declares merge() and raises NotImplementedError, :249-251) ----
+    def can_merge(self):
+        """W <- W + scale * B_s A_s is exact when no output stream needs the un-merged product: layers without task
+        adapters (qkv, every block but the last of a stage, MTLoRA+ reductions) and 'matrixv2' layers (whose task outputs
+        carry the shared update too, :267-274). 'matrix' layers with tasks need both W and W + sBA: they stay as they are."""
+        return self.r > 0 and hasattr(self, "lora_shared_A") and (self.tasks is None)
+
+    @torch.no_grad()
     def merge(self):
-        raise NotImplementedError
+        """Fold the shared adapter into the frozen weight (W = W + scale * B A) for evaluation; returns whether it did."""
+        if self.merged or not self.can_merge():
+            return False
+        sc = self.lora_shared_scale
+        sc = sc.detach().float() if isinstance(sc, torch.Tensor) else float(sc)
+        self.linear.weight.add_((self.lora_shared_B.float() @ self.lora_shared_A.float()) * sc)
+        self.merged = True
+        return True
+
+    @torch.no_grad()
+    def unmerge(self):
+        if not self.merged:
+            return False
+        sc = self.lora_shared_scale
+        sc = sc.detach().float() if isinstance(sc, torch.Tensor) else float(sc)
+        self.linear.weight.sub_((self.lora_shared_B.float() @ self.lora_shared_A.float()) * sc)
+        self.merged = False
+        return True
+
+    def train(self, mode: bool = True):
+        if mode and self.merged:
+            self.unmerge()      # adapters must see their own gradients again (loralib convention)
+        return super().train(mode)
+
+    @property
+    def engine(self):
+        """The engine the fused block drives: the full one, or a plain dense one while the shared adapter is merged."""
+        if self.merged:
+            if self._plain_engine is None:
+                self._plain_engine = LinearEngine(None, self.linear, ops.LinearSpec(self.linear.in_features,
+                                                                                      self.linear.out_features), None)
+            return self._plain_engine
+        return self._engine
 
     def forward(self, x: torch.Tensor, x_tasks: Optional[Dict[str, torch.Tensor]] = None):
-        return run_linear_standalone(self._engine, x, x_tasks, self.lora_dropout_p, self.training)
+        return run_linear_standalone(self.engine, x, x_tasks, self.lora_dropout_p, self.training)
 
 
 def mark_only_lora_as_trainable(model: nn.Module, bias: str = "none", freeze_patch_embed: bool = False,
@@ -358,6 +445,12 @@ def mark_only_lora_as_trainable(model: nn.Module, bias: str = "none", freeze_pat
                 m.bias.requires_grad = True
     else:
         raise NotImplementedError
+
+
+def merge_lora(model: nn.Module) -> int:
+    """Merge every mergeable MTLoRALinear of `model` (MTLoRALinear.merge) for evaluation; returns how many were merged.
+    `model.train()` un-merges them again."""
+    return sum(1 for m in model.modules() if isinstance(m, MTLoRALinear) and m.merge())
 
 
 def lora_filter(key: str, value: Any) -> bool:

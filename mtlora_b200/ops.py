@@ -19,6 +19,9 @@ def _chk(t, dtype, name):
         return
     if not t.is_cuda:
         raise RuntimeError(f"{name}: expected a CUDA tensor — mtlora_b200 has no CPU path")
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"{name}: tensor lives on {t.device} but the current CUDA device is "
+                           f"cuda:{torch.cuda.current_device()} (one process per GPU; wrap the call in torch.cuda.device)")
     if t.dtype != dtype:
         raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
     if not t.is_contiguous():
@@ -35,8 +38,8 @@ class LinearSpec:
     def __init__(self, in_features, out_features, r_shared=0, r_tasks=(), scale_shared=1.0, scale_tasks=(),
                  shared_mode="matrix"):
         self.K, self.Nf = int(in_features), int(out_features)
-        if shared_mode not in ("matrix", "matrixv2"):
-            raise NotImplementedError(f"mtlora_b200: shared_mode={shared_mode!r} is not implemented ('matrix', 'matrixv2' are)")
+        if shared_mode not in ("matrix", "matrixv2"):   # 'addition' is composed above the kernels (lora._AdditionTailFn)
+            raise ValueError(f"mtlora_b200: LinearSpec shared_mode must be 'matrix' or 'matrixv2', got {shared_mode!r}")
         self.mode = N.MTL_MODE_MATRIXV2 if shared_mode == "matrixv2" else N.MTL_MODE_MATRIX
         self.r_shared = int(r_shared)
         self.r_tasks = [int(r) for r in r_tasks] if self.r_shared > 0 else []

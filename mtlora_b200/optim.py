@@ -152,4 +152,7 @@ class FlatAdamW(torch.optim.Optimizer):
                    self._m.data_ptr(), self._v.data_ptr(), self._state.data_ptr(), groups, len(self.param_groups),
                    N.ptr(grad_scale), N.ptr(found_inf), self._sq.data_ptr() if clip else None,
                    float(self.max_grad_norm) if clip else 0.0, 1 if self.decoupled else 0, st)
+        # the kernel wrote the parameters through raw pointers: bump their autograd version counters, so that saved-tensor
+        # checks and the staged bf16 operand copies of the linears (keyed on (data_ptr, _version)) see the update
+        torch.autograd.graph.increment_version([p for p, k in zip(ps, key) if k])
         return loss

@@ -120,11 +120,54 @@ def _autocast_cuda_dtype():
 
 
 def _out_dtype(x):
-    """dtype handed back to the caller: the input dtype, or bf16 under autocast (what the reference's linears would
-    produce under `torch.autocast(dtype=bfloat16)`, main.py:341)."""
+    """dtype handed back to the caller: the input dtype, or the autocast dtype — what the reference's linears produce
+    under `torch.cuda.amp.autocast` (main.py:341: fp16 by default; bf16 in the BASELINE configs). The kernels compute
+    in bf16 with fp32 accumulation either way; under fp16 autocast the stage outputs are cast once at the boundary."""
     if torch.is_autocast_enabled():
-        return BF16
+        return _autocast_cuda_dtype()
     return x.dtype
+
+
+class _Slot:
+    """Placeholder of a tensor that travels through ctx.save_for_backward (index into ctx.saved_tensors)."""
+    __slots__ = ("i",)
+
+    def __init__(self, i):
+        self.i = i
+
+
+def _save_state(ctx, state):
+    """Store the (nested dict / list) backward state of a fused function: every tensor goes through
+    ctx.save_for_backward — so autograd's version-counter check catches in-place writes by downstream code (e.g. a
+    `relu_` on a stage output that a later stage saved as its input) and saved-tensor hooks / retain_graph work —
+    everything else is kept on ctx as is."""
+    tensors = []
+
+    def walk(o):
+        if torch.is_tensor(o):
+            tensors.append(o)
+            return _Slot(len(tensors) - 1)
+        if isinstance(o, dict):
+            return {k: walk(v) for k, v in o.items()}
+        if isinstance(o, (list, tuple)):
+            return type(o)(walk(v) for v in o)
+        return o
+    ctx.state_tree = walk(state)
+    ctx.save_for_backward(*tensors)
+
+
+def _load_state(ctx):
+    tensors = ctx.saved_tensors
+
+    def walk(o):
+        if isinstance(o, _Slot):
+            return tensors[o.i]
+        if isinstance(o, dict):
+            return {k: walk(v) for k, v in o.items()}
+        if isinstance(o, (list, tuple)):
+            return type(o)(walk(v) for v in o)
+        return o
+    return walk(ctx.state_tree)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -387,15 +430,14 @@ class _BlockFn(torch.autograd.Function):
         if need:
             ctx.blk = blk
             ctx.params = params
-            ctx.saved = dict(x=xb, mean1=mean1, rstd1=rstd1, sv_q=sv_q, qkv=qkv, lse=lse, rpb=rpb, sv_p=sv_p, x1=x1,
-                             mean2=mean2, rstd2=rstd2, sv_1=sv_1, g=g, sv_2=sv_2, n1w=n1w, n2w=n2w, S=S,
-                             dims=(B, L, C, H, W), in_dtype=x.dtype)
+            _save_state(ctx, dict(x=xb, mean1=mean1, rstd1=rstd1, sv_q=sv_q, qkv=qkv, lse=lse, rpb=rpb, sv_p=sv_p, x1=x1,
+                                  mean2=mean2, rstd2=rstd2, sv_1=sv_1, g=g, sv_2=sv_2, n1w=n1w, n2w=n2w, S=S,
+                                  dims=(B, L, C, H, W), in_dtype=x.dtype))
         return tuple(y[j].view(B, L, C) for j in range(S))
 
     @staticmethod
     def backward(ctx, *dys):
-        blk, sv = ctx.blk, ctx.saved
-        ctx.saved = None
+        blk, sv = ctx.blk, _load_state(ctx)
         B, L, C, H, W = sv["dims"]
         M, S = B * L, sv["S"]
         attn = blk.attn
@@ -405,13 +447,25 @@ class _BlockFn(torch.autograd.Function):
         grads = {}
         # fc2 -> d(fc1 pre-activation), GELU' fused into the epilogue
         dg, g2 = e_fc2.backward(sv["sv_2"], dy, gelu_aux=sv["g"], aux_is_grad=True)
-        if dys[0] is None and S > 1 and e_fc2.spec.r_shared > 0 and e_fc2.spec.mode == ops.N.MTL_MODE_MATRIX:
-            # the shared output stream is unused downstream (last stage, reference quirk: its fc2.lora_shared_{A,B}
-            # receive no gradient at all) -> report None like autograd does, not zeros
-            fc2 = blk.mlp.fc2
-            g2.pop(fc2.lora_shared_A, None)
-            g2.pop(fc2.lora_shared_B, None)
         grads.update(g2)
+        dead = []   # parameters that feed ONLY output streams nobody used: autograd reports None for them, not zeros
+        if S > 1 and e_fc2.spec.r_shared > 0 and e_fc2.spec.mode == ops.N.MTL_MODE_MATRIX:
+            fc2 = blk.mlp.fc2
+            if dys[0] is None:
+                # the shared output stream is unused downstream (last stage, reference quirk 8: its
+                # fc2.lora_shared_{A,B} receive no gradient at all; every other shared adapter still feeds the frozen
+                # product of the task outputs, lora.py:255,262-266)
+                dead += [fc2.lora_shared_A, fc2.lora_shared_B]
+            for j, t in enumerate(blk.tasks):
+                if dys[1 + j] is None:
+                    # INTERMEDIATE_SPECIALIZATION (:53,175,544-545): the task streams of every block but the last of a
+                    # stage are computed and dropped; their adapters form a chain that reaches no other output
+                    for lay in (attn.proj, blk.mlp.fc1, fc2):
+                        if getattr(lay, "lora_tasks_A", None) is not None and t in lay.lora_tasks_A:
+                            dead += [lay.lora_tasks_A[t], lay.lora_tasks_B[t]]
+                        ts = getattr(lay, "lora_task_scale", None)
+                        if isinstance(ts, nn.ParameterDict):
+                            dead.append(ts[t])
         dh2, g1 = e_fc1.backward(sv["sv_1"], dg)
         grads.update(g1)
         del dg
@@ -443,6 +497,8 @@ class _BlockFn(torch.autograd.Function):
         dx = dx.view(B, L, C)
         if sv["in_dtype"] != BF16:
             dx = dx.to(sv["in_dtype"])
+        for p in dead:
+            grads.pop(p, None)
         out = []
         for p in ctx.params:
             gr = grads.get(p) if p.requires_grad else None
@@ -506,14 +562,16 @@ class SwinTransformerBlock(nn.Module):
 
     # ---- fused path ----------------------------------------------------------------------------------------------
     def _fused_params(self):
-        if self._param_list is None:
-            a, m = self.attn, self.mlp
+        a, m = self.attn, self.mlp
+        engs = (_engine_of(a.qkv), _engine_of(a.proj), _engine_of(m.fc1), _engine_of(m.fc2))
+        key = tuple(id(e) for e in engs)      # MTLoRALinear.merge() swaps the engine in effect
+        if self._param_list is None or self._param_list[0] != key:
             ps = [self.norm1.weight, self.norm1.bias, a.relative_position_bias_table]
-            ps += _engine_of(a.qkv).params() + _engine_of(a.proj).params()
+            ps += engs[0].params() + engs[1].params()
             ps += [self.norm2.weight, self.norm2.bias]
-            ps += _engine_of(m.fc1).params() + _engine_of(m.fc2).params()
-            self._param_list = ps
-        return self._param_list
+            ps += engs[2].params() + engs[3].params()
+            self._param_list = (key, ps)
+        return self._param_list[1]
 
     def _fusable(self):
         a, m = self.attn, self.mlp
@@ -525,6 +583,8 @@ class SwinTransformerBlock(nn.Module):
             return False
         if self.dim != 32 * self.num_heads or self.window_size > 8:
             return False
+        if any(_engine_of(l).addition for l in (a.qkv, a.proj, m.fc1, m.fc2)):
+            return False    # 'addition' mode: LayerNorm of the task sum between the layers -> composed path
         es = [_engine_of(a.proj).spec, _engine_of(m.fc1).spec, _engine_of(m.fc2).spec]
         # all three task-bearing layers agree on the number of streams and on having adapters (every shipped YAML)
         if len({e.S_out for e in es}) != 1 or len({e.r_shared > 0 for e in es[1:]}) != 1:
@@ -659,15 +719,14 @@ class _PatchMergeFn(torch.autograd.Function):
         y, _, sv = eng.forward(h.view(-1, rows, 4 * C), dropout_p=p, seed=seed, save=need)
         if need:
             ctx.pm, ctx.params = pm, params
-            ctx.saved = dict(x=x, mean=mean, rstd=rstd, nw=nw, sv=sv, dims=(S, B, L, C, H, W),
-                             in_dtypes=[t.dtype for t in xs])
+            _save_state(ctx, dict(x=x, mean=mean, rstd=rstd, nw=nw, sv=sv, dims=(S, B, L, C, H, W),
+                                  in_dtypes=[t.dtype for t in xs]))
         y = y.view(S, B, L // 4, 2 * C)
         return tuple(y[j] for j in range(S))
 
     @staticmethod
     def backward(ctx, *dys):
-        pm, sv = ctx.pm, ctx.saved
-        ctx.saved = None
+        pm, sv = ctx.pm, _load_state(ctx)
         S, B, L, C, H, W = sv["dims"]
         rows = S * B * L // 4
         eng = _engine_of(pm.reduction)

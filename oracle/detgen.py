@@ -41,7 +41,7 @@ def std_uniform(name, shape, std, mean=0.0):
     return uniform(name, shape, mean - a, mean + a)
 
 
-def backbone_param_shapes(cfg, ranks, downsampler_lora=False, qkv_bias=True):
+def backbone_param_shapes(cfg, ranks, downsampler_lora=False, qkv_bias=True, intermediate_specialization=False):
     """name -> shape for every parameter of SwinTransformerMTLoRA(num_classes=0), in the reference's
     named_parameters() naming (SURVEY.md §5 checkpoint row; validated against the real model by
     tests/golden/make_golden.py). `ranks[s]` = {'shared': r_s, task: r_t, ...} = mtlora.R_PER_TASK_LIST[s]."""
@@ -73,7 +73,7 @@ def backbone_param_shapes(cfg, ranks, downsampler_lora=False, qkv_bias=True):
         w = min(ws, res // 2 ** s)
         for i in range(depth):
             b = f"layers.{s}.blocks.{i}."
-            last = i == depth - 1
+            last = i == depth - 1 or intermediate_specialization
             out[b + "norm1.weight"] = (C,)
             out[b + "norm1.bias"] = (C,)
             out[b + "attn.relative_position_bias_table"] = ((2 * w - 1) ** 2, cfg.num_heads[s])

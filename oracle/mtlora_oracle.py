@@ -44,6 +44,7 @@ class OracleConfig:
     dropout: Sequence[float] = (0.0, 0.0, 0.0, 0.0)               # mtlora.DROPOUT[stage]
     drop_path_rate: float = 0.0
     shared_mode: str = "matrix"
+    intermediate_specialization: bool = False                     # mtlora.INTERMEDIATE_SPECIALIZATION (:53,61,175)
     training: bool = False
     ln_eps: float = 1e-5
 
@@ -81,12 +82,21 @@ def mtlora_linear(p, prefix, x, x_tasks=None, tasks=None, scale_shared=1.0, scal
     W = p[prefix + "linear.weight"] if (prefix + "linear.weight") in p else p[prefix + "weight"]
     b = p.get(prefix + "linear.bias", p.get(prefix + "bias"))
     pretrained = F.linear(x, W, b)                                             # lora.py:255
-    if (prefix + "lora_shared_A") not in p:
+    has_tasks = tasks is not None and (prefix + "lora_tasks_A." + tasks[0]) in p
+    if (prefix + "lora_shared_A") not in p and not has_tasks:
         return pretrained, None
     xd = F.dropout(x, dropout, training) if dropout > 0 else x                 # lora.py:258
+    if (prefix + "lora_norm.weight") in p:                                     # shared_mode 'addition', lora.py:275-282
+        lora_tasks = {}
+        for t in tasks:
+            xin = xd if x_tasks is None else x_tasks[t]
+            At, Bt = p[prefix + "lora_tasks_A." + t], p[prefix + "lora_tasks_B." + t]
+            lora_tasks[t] = pretrained + (xin @ At.t() @ Bt.t()) * scale_tasks[t]
+        tot = torch.stack(list(lora_tasks.values()), 0).sum(0)
+        lora = F.layer_norm(tot, (tot.shape[-1],), p[prefix + "lora_norm.weight"], p[prefix + "lora_norm.bias"], 1e-5)
+        return pretrained + lora, lora_tasks
     A, B = p[prefix + "lora_shared_A"], p[prefix + "lora_shared_B"]
     lora = (xd @ A.t() @ B.t()) * scale_shared                                 # lora.py:260-261
-    has_tasks = tasks is not None and (prefix + "lora_tasks_A." + tasks[0]) in p
     lora_tasks = None
     if has_tasks:
         lora_tasks = {}
@@ -248,7 +258,8 @@ def basic_layer(p, prefix, x, H, W, depth, num_heads, cfg, stage, dpr, has_downs
     tasks_lora = None
     for i in range(depth):
         x, tasks_lora = swin_block(p, f"{prefix}blocks.{i}.", x, H, W, num_heads, cfg.window_size,
-                                   0 if i % 2 == 0 else cfg.window_size // 2, cfg, stage, i == depth - 1, dpr[i])
+                                   0 if i % 2 == 0 else cfg.window_size // 2, cfg, stage,
+                                   i == depth - 1 or cfg.intermediate_specialization, dpr[i])
     if has_downsample:
         x = patch_merging(p, prefix + "downsample.", x, H, W, cfg, stage)
         if tasks_lora is not None:

@@ -17,3 +17,11 @@ def golden():
     import numpy as np
     path = os.path.join(ROOT, "tests", "golden", "reference_vectors.npz")
     return np.load(path, allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def headline():
+    """Golden vectors of the configurations the headline numbers are quoted on + addition mode (make_golden.headline)."""
+    import numpy as np
+    path = os.path.join(ROOT, "tests", "golden", "headline_vectors.npz")
+    return np.load(path, allow_pickle=False)

@@ -73,6 +73,136 @@ def sample(t, stride=101):
     return np.concatenate([[f.sum().item(), f.abs().sum().item(), float(f.numel())], f[::stride].numpy()]).astype(np.float64)
 
 
+HEADLINE_TASKS6 = ["semseg", "normals", "sal", "human_parts", "depth", "edge"]
+# tag -> ctor arguments of the backbone cases the headline numbers are quoted on (BASELINE.json configs[1..4])
+HEADLINE_CASES = {
+    # configs[1]: Swin-T 448, 4 tasks, r 64 / 4 (configs/mtlora/tiny_448/mtlora_tiny_448_r64_scale4_pertask.yaml)
+    "h_t448": dict(img=448, embed_dim=96, depths=[2, 2, 6, 2], heads=[3, 6, 12, 24], n_tasks=4, r_s=64, r_t=4, B=1),
+    # configs[2]: Swin-S 448, 4 tasks, r 64 / 4
+    "h_s448": dict(img=448, embed_dim=96, depths=[2, 2, 18, 2], heads=[3, 6, 12, 24], n_tasks=4, r_s=64, r_t=4, B=1),
+    # configs[3]: Swin-B 448, 6 tasks, r 32 / 4
+    "h_b448": dict(img=448, embed_dim=128, depths=[2, 2, 18, 2], heads=[4, 8, 16, 32], n_tasks=6, r_s=32, r_t=4, B=1),
+    # configs[4] / non-pertask YAMLs: all-equal ranks of 64 (rank space 5 x 64 = 320 columns)
+    "h_t224_r64all": dict(img=224, embed_dim=96, depths=[2, 2, 6, 2], heads=[3, 6, 12, 24], n_tasks=4, r_s=64, r_t=64, B=2),
+    # INTERMEDIATE_SPECIALIZATION=True (swin_transformer_mtlora.py:53,175): every block carries the task adapters
+    "h_t224_interm": dict(img=224, embed_dim=96, depths=[2, 2, 2, 2], heads=[3, 6, 12, 24], n_tasks=2, r_s=16, r_t=4, B=2,
+                          interm=True),
+    # MTLoRA+ (DOWNSAMPLER_ENABLED=True: the reductions are frozen and carry a shared adapter)
+    "h_t224_plus": dict(img=224, embed_dim=96, depths=[2, 2, 2, 2], heads=[3, 6, 12, 24], n_tasks=2, r_s=16, r_t=4, B=2,
+                        downsampler=True),
+}
+
+
+def headline_build(mod, case, ns_fn):
+    """Backbone of `case` from module `mod` (the reference's or mtlora_b200's swin_transformer_mtlora)."""
+    import contextlib
+    import io
+    c = HEADLINE_CASES[case]
+    tasks = HEADLINE_TASKS6[:c["n_tasks"]]
+    ranks = [dict({"shared": c["r_s"]}, **{t: c["r_t"] for t in tasks})] * 4
+    ns = ns_fn(ranks, tasks, downsampler=c.get("downsampler", False))
+    ns.INTERMEDIATE_SPECIALIZATION = c.get("interm", False)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = mod.SwinTransformerMTLoRA(img_size=c["img"], patch_size=4, in_chans=3, num_classes=0,
+                                        embed_dim=c["embed_dim"], depths=c["depths"], num_heads=c["heads"],
+                                        window_size=7, mlp_ratio=4.0, qkv_bias=True, drop_rate=0.0, drop_path_rate=0.0,
+                                        ape=False, patch_norm=True, tasks=tasks, mtlora=ns)
+    return net, tasks
+
+
+def sample32(t, stride):
+    """(float64 [sum, sum |.|, numel], float32 strided sample) of a tensor."""
+    f = t.detach().reshape(-1).double().cpu()
+    return np.array([f.sum().item(), f.abs().sum().item(), float(f.numel())]), f[::stride].float().numpy()
+
+
+HEADLINE_TRAINABLE = ("lora_", "norm", "relative_position_bias_table", "downsample.reduction", "patch_embed")
+
+
+def headline(ref, MTLoRALinear):
+    """Golden vectors of the configurations the headline numbers are quoted on -> tests/golden/headline_vectors.npz
+    (samples: every 101st element of each stage tensor, every 53rd of each trainable gradient, plus sums)."""
+    G = {}
+    for case, c in HEADLINE_CASES.items():
+        net, tasks = headline_build(ref, case, mtlora_ns)
+        net.eval()
+        load_det(net)
+        img = detgen.uniform(case + ".img", (c["B"], 3, c["img"], c["img"]), -2.0, 2.0)
+        stages = net(img, return_stages=True)
+        loss = sum(v.pow(2).mean() for _, tl in stages for v in tl.values())
+        loss.backward()
+        G[f"{case}/loss"] = np.array([loss.item()])
+        for s, (xs, tl) in enumerate(stages):
+            G[f"{case}/stage{s}.x.stat"], G[f"{case}/stage{s}.x"] = sample32(xs, 101)
+            for t in tasks:
+                G[f"{case}/stage{s}.{t}.stat"], G[f"{case}/stage{s}.{t}"] = sample32(tl[t], 101)
+        none_grads = []
+        for name, prm in net.named_parameters():
+            if prm.grad is None:
+                none_grads.append(name)
+            elif any(k in name for k in HEADLINE_TRAINABLE):
+                G[f"{case}/d.{name}.stat"], G[f"{case}/d.{name}"] = sample32(prm.grad, 53)
+        G[f"{case}/none_grads"] = np.array(none_grads)
+        print(f"  {case}: loss {loss.item():.6f}, {sum(1 for k in G if k.startswith(case + '/d.')) // 2} gradient tensors")
+        del net, stages, loss
+
+    # shared_mode='addition' (lora.py:275-282 + lora_norm :217-219): layer level and inside a block
+    tasks = ["normals", "semseg"]
+    for tag, K, N, r, xt in [("lin_add_tasks", 96, 96, {"shared": 16, "normals": 4, "semseg": 4}, False),
+                             ("lin_add_xtasks", 96, 384, {"shared": 16, "normals": 4, "semseg": 8}, True)]:
+        m = MTLoRALinear(K, N, r=r, lora_shared_scale=4.0, lora_task_scale={t: 2.0 + i for i, t in enumerate(tasks)},
+                         lora_dropout=0.0, tasks=tasks, shared_mode="addition")
+        load_det(m, tag + ".")
+        x = detgen.uniform(tag + ".x", (2, 49, K)).requires_grad_()
+        x_tasks = {t: detgen.uniform(f"{tag}.x.{t}", (2, 49, K)).requires_grad_() for t in tasks} if xt else None
+        y, yt = m(x, x_tasks)
+        loss = (y * detgen.uniform(tag + ".gy", tuple(y.shape))).sum()
+        for t in tasks:
+            loss = loss + (yt[t] * detgen.uniform(f"{tag}.gy.{t}", tuple(y.shape))).sum()
+        loss.backward()
+        G[tag + "/y"] = y.detach().numpy()
+        for t in tasks:
+            G[f"{tag}/y.{t}"] = yt[t].detach().numpy()
+        G[tag + "/dx"] = x.grad.numpy()
+        if xt:
+            for t in tasks:
+                G[f"{tag}/dx.{t}"] = x_tasks[t].grad.numpy()
+        G[tag + "/param_names"] = np.array([n for n, _ in m.named_parameters()])
+        for name, prm in m.named_parameters():
+            if prm.grad is not None and "lora" in name:
+                G[f"{tag}/d.{name}"] = prm.grad.numpy()
+    ranks1 = [{"shared": 8, "normals": 4, "semseg": 4}]
+    tag = "blk_add"
+    import contextlib
+    import io
+    ns = mtlora_ns(ranks1, tasks)
+    ns.SHARED_MODE = "addition"
+    with contextlib.redirect_stdout(io.StringIO()):
+        blk = ref.SwinTransformerBlock(dim=96, input_resolution=(14, 14), num_heads=3, window_size=7, shift_size=3,
+                                       lora=True, tasks=tasks, mtlora=ns, layer_idx=0)
+    blk.eval()
+    load_det(blk, tag + ".")
+    x = detgen.uniform(tag + ".x", (2, 196, 96)).requires_grad_()
+    y, yt = blk(x)
+    loss = (y * detgen.uniform(tag + ".gy", tuple(y.shape))).sum()
+    for t in tasks:
+        loss = loss + (yt[t] * detgen.uniform(f"{tag}.gy.{t}", tuple(y.shape))).sum()
+    loss.backward()
+    G[tag + "/y"] = y.detach().numpy()
+    for t in tasks:
+        G[f"{tag}/y.{t}"] = yt[t].detach().numpy()
+    G[tag + "/dx"] = x.grad.numpy()
+    G[tag + "/param_names"] = np.array([n for n, _ in blk.named_parameters()])
+    for name, prm in blk.named_parameters():
+        if prm.grad is not None and ("lora" in name or "norm" in name or "relative_position" in name):
+            G[f"{tag}/d.{name}"] = prm.grad.numpy()
+
+    out = os.path.join(ROOT, "tests", "golden", "headline_vectors.npz")
+    np.savez_compressed(out, **{k: (v.astype(np.float32) if v.dtype == np.float64 and not (k.endswith(".stat") or k.endswith("/loss")) else v)
+                                for k, v in G.items()})
+    print(f"wrote {out}: {len(G)} arrays, {os.path.getsize(out) / 1e6:.2f} MB")
+
+
 def main():
     install_stubs()
     sys.path.insert(0, REF)
@@ -211,6 +341,9 @@ def main():
     shapes2 = detgen.backbone_param_shapes(cfg, ranks, downsampler_lora=True)
     got2 = {n: tuple(p.shape) for n, p in net2.named_parameters()}
     assert list(got2.keys()) == list(shapes2.keys()) and got2 == dict(shapes2)
+
+    if os.environ.get("MTLORA_GOLDEN_SKIP_HEADLINE", "0") != "1":
+        headline(ref, MTLoRALinear)
 
     out = os.path.join(ROOT, "tests", "golden", "reference_vectors.npz")
     np.savez_compressed(out, **{k: (v.astype(np.float32) if v.dtype == np.float64 and not k.startswith("c1/") else v)

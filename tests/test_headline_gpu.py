@@ -1,0 +1,430 @@
+"""GPU parity on the configurations the headline numbers are quoted on (BASELINE.json configs[1..4]) and on the mode
+switches of the YAML surface, against
+ (a) tests/golden/headline_vectors.npz — outputs / gradients of the UNMODIFIED reference (tests/golden/make_golden.py), and
+ (b) the unmodified reference itself run live on the same GPU in fp32 (baseline/_ref, when installed).
+Tolerances (bf16 compute, fp32 accumulation; north_star: 1e-2 bf16), all relative to the tensor's max magnitude:
+  loss 1e-2; stage outputs 1e-2 ... listed per case in TOL; trainable gradients 2e-2 (sums over up to 12,544 tokens per
+  image of bf16-rounded products) + 1e-5 absolute for LayerNorm-weight gradients that cancel to ~1e-4 of their summands.
+"""
+import contextlib
+import io
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import detgen
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+TASKS6 = ["semseg", "normals", "sal", "human_parts", "depth", "edge"]
+CASES = {   # mirrors tests/golden/make_golden.py::HEADLINE_CASES
+    "h_t448": dict(img=448, embed_dim=96, depths=[2, 2, 6, 2], heads=[3, 6, 12, 24], n_tasks=4, r_s=64, r_t=4, B=1),
+    "h_s448": dict(img=448, embed_dim=96, depths=[2, 2, 18, 2], heads=[3, 6, 12, 24], n_tasks=4, r_s=64, r_t=4, B=1),
+    "h_b448": dict(img=448, embed_dim=128, depths=[2, 2, 18, 2], heads=[4, 8, 16, 32], n_tasks=6, r_s=32, r_t=4, B=1),
+    "h_t224_r64all": dict(img=224, embed_dim=96, depths=[2, 2, 6, 2], heads=[3, 6, 12, 24], n_tasks=4, r_s=64, r_t=64, B=2),
+    "h_t224_interm": dict(img=224, embed_dim=96, depths=[2, 2, 2, 2], heads=[3, 6, 12, 24], n_tasks=2, r_s=16, r_t=4, B=2,
+                          interm=True),
+    "h_t224_plus": dict(img=224, embed_dim=96, depths=[2, 2, 2, 2], heads=[3, 6, 12, 24], n_tasks=2, r_s=16, r_t=4, B=2,
+                        downsampler=True),
+}
+# stage-output tolerance per case: 1e-2 (north_star) except the 18-block stages of Swin-S / Swin-B, where 22 residual
+# blocks of bf16 rounding accumulate before stage 2's output (measured ~1.2e-2; every block adds ~2^-9 relative noise)
+TOL_ACT = {"h_s448": 2e-2, "h_b448": 2e-2}
+TOL_GRAD = 2e-2
+
+
+@pytest.fixture(scope="module")
+def S():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from mtlora_b200 import swin_transformer_mtlora as _S
+    return _S
+
+
+def mtlora_ns(ranks, tasks, dropout=0.0, downsampler=False, scale=4.0, **over):
+    n = len(ranks)
+    d = dict(R_PER_TASK_LIST=ranks, SHARED_SCALE=[scale] * n, SCALE_PER_TASK_LIST=[{t: scale for t in tasks} for _ in range(n)],
+             DROPOUT=[dropout] * n, TRAINABLE_SCALE_SHARED=False, TRAINABLE_SCALE_PER_TASK=False, SHARED_MODE="matrix",
+             INTERMEDIATE_SPECIALIZATION=False, QKV_ENABLED=True, PROJ_ENABLED=True, FC1_ENABLED=True, FC2_ENABLED=True,
+             DOWNSAMPLER_ENABLED=downsampler)
+    d.update(over)
+    return types.SimpleNamespace(**d)
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def build(mod, case, dropout=0.0, drop_path=0.0):
+    c = CASES[case]
+    tasks = TASKS6[:c["n_tasks"]]
+    ranks = [dict({"shared": c["r_s"]}, **{t: c["r_t"] for t in tasks})] * 4
+    ns = mtlora_ns(ranks, tasks, dropout=dropout, downsampler=c.get("downsampler", False),
+                   INTERMEDIATE_SPECIALIZATION=c.get("interm", False))
+    net = quiet(mod.SwinTransformerMTLoRA, img_size=c["img"], patch_size=4, in_chans=3, num_classes=0,
+                embed_dim=c["embed_dim"], depths=c["depths"], num_heads=c["heads"], window_size=7, mlp_ratio=4.0,
+                qkv_bias=True, drop_rate=0.0, drop_path_rate=drop_path, ape=False, patch_norm=True, tasks=tasks, mtlora=ns)
+    return net, tasks
+
+
+def load_det(module, prefix=""):
+    with torch.no_grad():
+        for name, prm in module.named_parameters():
+            prm.copy_(detgen.param_value(prefix + name, tuple(prm.shape)))
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30), np.abs(a - b).max()
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_backbone_headline_vs_reference_golden(S, headline, case):
+    """Loss, every stage tensor of every stream and every trainable gradient (adapters, LayerNorms, rel-pos tables,
+    downsample.reduction, patch_embed) of the fused CUDA path vs the unmodified reference's own numbers."""
+    c = CASES[case]
+    net, tasks = build(S, case)
+    load_det(net)
+    net.cuda().eval()
+    img = detgen.uniform(case + ".img", (c["B"], 3, c["img"], c["img"]), -2.0, 2.0).cuda()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        stages = net(img, return_stages=True)
+    loss = sum(v.float().pow(2).mean() for _, tl in stages for v in tl.values())
+    loss.backward()
+    g0 = headline[f"{case}/loss"][0]
+    assert abs(loss.item() - g0) <= 1e-2 * abs(g0), (loss.item(), g0)
+    tol = TOL_ACT.get(case, 1e-2)
+    worst_act = 0.0
+    for s, (xs, tl) in enumerate(stages):
+        for name, t in [(f"{case}/stage{s}.x", xs)] + [(f"{case}/stage{s}.{k}", tl[k]) for k in tasks]:
+            f = t.detach().reshape(-1).double().cpu()
+            stat = headline[name + ".stat"]
+            assert stat[2] == f.numel(), name
+            r, _ = rel(f[::101].numpy(), headline[name])
+            worst_act = max(worst_act, r)
+            assert r <= tol, f"{name}: {r:.3e} > {tol}"
+            assert abs(f.abs().sum().item() - stat[1]) <= 1e-2 * stat[1], name
+    none = sorted(n for n, v in net.named_parameters() if v.grad is None)
+    assert none == sorted(headline[f"{case}/none_grads"].tolist())
+    checked, worst, over = 0, 0.0, []
+    for n, v in net.named_parameters():
+        key = f"{case}/d.{n}"
+        if key in headline.files:
+            r, err = rel(v.grad.reshape(-1)[::53].double().cpu().numpy(), headline[key])
+            if err > 1e-5:
+                worst = max(worst, r)
+                if r > TOL_GRAD:
+                    over.append((n, r))
+            checked += 1
+    print(f"{case}: loss rel {abs(loss.item() - g0) / abs(g0):.2e}, worst stage tensor {worst_act:.3e}, "
+          f"{checked} gradient tensors, worst rel-to-max {worst:.3e}")
+    assert checked > 150
+    assert not over, f"gradients beyond {TOL_GRAD}: {over[:8]}"
+
+
+def test_live_reference_on_gpu_config2(S):
+    """north_star: "outputs matching the reference PyTorch path on identical synthetic 448x448 batches within 1e-2
+    (bf16)". The unmodified reference (baseline/_ref) runs in fp32 on the same GPU, batch 2, full tensors compared."""
+    from baseline import refload
+    if not refload.available():
+        pytest.skip("baseline/_ref not installed (python baseline/install_reference.py)")
+    ref = refload.load()
+    rnet, tasks = build(ref.swin, "h_t448")
+    load_det(rnet)
+    rnet.cuda().eval()
+    net, _ = build(S, "h_t448")
+    net.load_state_dict(rnet.state_dict())            # drop-in: the reference's checkpoint loads as is
+    net.cuda().eval()
+    img = torch.randn(2, 3, 448, 448, generator=torch.Generator().manual_seed(11)).cuda()
+    rs = rnet(img, return_stages=True)
+    rloss = sum(v.pow(2).mean() for _, tl in rs for v in tl.values())
+    rloss.backward()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        gs = net(img, return_stages=True)
+    loss = sum(v.float().pow(2).mean() for _, tl in gs for v in tl.values())
+    loss.backward()
+    assert abs(loss.item() - rloss.item()) <= 1e-2 * abs(rloss.item())
+    for s in range(4):
+        for k in [None] + tasks:
+            a = gs[s][0] if k is None else gs[s][1][k]
+            b = rs[s][0] if k is None else rs[s][1][k]
+            r, _ = rel(a.detach().float().cpu().numpy(), b.detach().cpu().numpy())
+            assert r <= 1e-2, (s, k, r)
+    rg = dict(rnet.named_parameters())
+    worst = 0.0
+    for n, v in net.named_parameters():
+        if rg[n].grad is None:
+            assert v.grad is None, n
+            continue
+        if any(t in n for t in ("lora_", "norm", "relative_position_bias_table", "downsample.reduction", "patch_embed")):
+            r, err = rel(v.grad.float().cpu().numpy(), rg[n].grad.cpu().numpy())
+            if err > 1e-5:
+                worst = max(worst, r)
+                assert r <= TOL_GRAD, (n, r)
+    print(f"live reference, config 2 batch 2: worst gradient rel-to-max {worst:.3e}")
+
+
+TASKS2 = ["normals", "semseg"]
+
+
+def close(a, b, tol, what):
+    r, _ = rel(a.detach().float().cpu().numpy(), b)
+    assert r <= tol, f"{what}: {r:.3e} > {tol}"
+
+
+@pytest.mark.parametrize("tag,K,N,r,xt", [("lin_add_tasks", 96, 96, {"shared": 16, "normals": 4, "semseg": 4}, False),
+                                          ("lin_add_xtasks", 96, 384, {"shared": 16, "normals": 4, "semseg": 8}, True)])
+def test_mtlora_linear_addition_mode(S, headline, tag, K, N, r, xt):
+    """shared_mode='addition' (lora.py:275-282): parameter surface and numbers vs the reference."""
+    from mtlora_b200.lora import MTLoRALinear
+    m = MTLoRALinear(K, N, r=r, lora_shared_scale=4.0, lora_task_scale={t: 2.0 + i for i, t in enumerate(TASKS2)},
+                     lora_dropout=0.0, tasks=TASKS2, shared_mode="addition")
+    assert [n for n, _ in m.named_parameters()] == headline[tag + "/param_names"].tolist()
+    load_det(m, tag + ".")
+    m.cuda()
+    x = detgen.uniform(tag + ".x", (2, 49, K)).cuda().requires_grad_()
+    x_tasks = {t: detgen.uniform(f"{tag}.x.{t}", (2, 49, K)).cuda().requires_grad_() for t in TASKS2} if xt else None
+    y, yt = m(x, x_tasks)
+    loss = (y * detgen.uniform(tag + ".gy", tuple(y.shape)).cuda()).sum()
+    for t in TASKS2:
+        loss = loss + (yt[t] * detgen.uniform(f"{tag}.gy.{t}", tuple(y.shape)).cuda()).sum()
+    loss.backward()
+    close(y, headline[tag + "/y"], 1e-2, "y")
+    for t in TASKS2:
+        close(yt[t], headline[f"{tag}/y.{t}"], 1e-2, "y." + t)
+    close(x.grad, headline[tag + "/dx"], 1e-2, "dx")
+    if xt:
+        for t in TASKS2:
+            close(x_tasks[t].grad, headline[f"{tag}/dx.{t}"], 1e-2, "dx." + t)
+    for n, v in m.named_parameters():
+        if "lora" in n:
+            close(v.grad, headline[f"{tag}/d.{n}"], 2e-2, "d." + n)
+
+
+def test_swin_block_addition_mode(S, headline):
+    tag = "blk_add"
+    ranks1 = [{"shared": 8, "normals": 4, "semseg": 4}]
+    blk = quiet(S.SwinTransformerBlock, dim=96, input_resolution=(14, 14), num_heads=3, window_size=7, shift_size=3,
+                lora=True, tasks=TASKS2, mtlora=mtlora_ns(ranks1, TASKS2, SHARED_MODE="addition"), layer_idx=0)
+    assert [n for n, _ in blk.named_parameters()] == headline[tag + "/param_names"].tolist()
+    assert not blk._fusable()
+    blk.eval()
+    load_det(blk, tag + ".")
+    blk.cuda()
+    x = detgen.uniform(tag + ".x", (2, 196, 96)).cuda().requires_grad_()
+    y, yt = blk(x)
+    loss = (y * detgen.uniform(tag + ".gy", tuple(y.shape)).cuda()).sum()
+    for t in TASKS2:
+        loss = loss + (yt[t] * detgen.uniform(f"{tag}.gy.{t}", tuple(y.shape)).cuda()).sum()
+    loss.backward()
+    close(y, headline[tag + "/y"], 1e-2, "y")
+    for t in TASKS2:
+        close(yt[t], headline[f"{tag}/y.{t}"], 1e-2, "y." + t)
+    close(x.grad, headline[tag + "/dx"], 1e-2, "dx")
+    n_checked = 0
+    for n, v in blk.named_parameters():
+        key = f"{tag}/d.{n}"
+        if key in headline.files:
+            close(v.grad, headline[key], 2e-2, "d." + n)
+            n_checked += 1
+    assert n_checked >= 20
+
+
+def test_merge_for_inference(S):
+    """MTLoRALinear.merge: W <- W + scale B A on every layer without task adapters; same outputs."""
+    from mtlora_b200.lora import MTLoRALinear, merge_lora
+    net, tasks = build(S, "h_t224_interm".replace("interm", "plus"))
+    load_det(net)
+    net.cuda().eval()
+    img = detgen.uniform("merge.img", (2, 3, 224, 224), -2.0, 2.0).cuda()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        before = net(img, return_stages=True)
+    w0 = net.layers[0].blocks[0].attn.qkv.linear.weight.detach().clone()
+    n = merge_lora(net)
+    mergeable = sum(1 for m in net.modules() if isinstance(m, MTLoRALinear) and m.tasks is None)
+    assert n == mergeable and n >= 4 * 2 + 4 * 3 + 3       # qkv everywhere, the non-last blocks, the MTLoRA+ reductions
+    assert not torch.equal(w0, net.layers[0].blocks[0].attn.qkv.linear.weight)
+    assert merge_lora(net) == 0
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        after = net(img, return_stages=True)
+    for (xa, ta), (xb, tb) in zip(before, after):
+        close(xb, xa.float().cpu().numpy(), 1e-2, "merged stage x")
+        for t in tasks:
+            close(tb[t], ta[t].float().cpu().numpy(), 1e-2, "merged stage " + t)
+    net.train()                                                 # un-merges (loralib convention)
+    assert torch.allclose(w0, net.layers[0].blocks[0].attn.qkv.linear.weight, atol=1e-6)
+
+
+def test_fp16_autocast_grad_scaler_step(S):
+    """The reference's default AMP (main.py:341 fp16 autocast + utils.py:352 GradScaler): stage outputs come back in
+    fp16, the 65536x-scaled loss passes through the fused backward unharmed (gradients == scale x the unscaled ones)."""
+    net, tasks = build(S, "h_t224_plus")
+    load_det(net)
+    net.cuda().eval()
+    img = detgen.uniform("fp16.img", (2, 3, 224, 224), -2.0, 2.0).cuda()
+
+    def run(dtype, scale):
+        for p in net.parameters():
+            p.grad = None
+        with torch.autocast("cuda", dtype=dtype):
+            st = net(img, return_stages=True)
+        assert st[0][0].dtype == dtype and st[3][1][tasks[0]].dtype == dtype
+        loss = sum(v.float().pow(2).mean() for _, tl in st for v in tl.values())
+        (loss * scale).backward()
+        return loss.item(), {n: p.grad.detach().clone() for n, p in net.named_parameters() if p.grad is not None}
+    l0, g0 = run(torch.bfloat16, 1.0)
+    l1, g1 = run(torch.float16, 65536.0)
+    assert abs(l0 - l1) <= 2e-3 * abs(l0)
+    assert g0.keys() == g1.keys()
+    for n in g0:
+        assert torch.isfinite(g1[n]).all(), n
+        r, err = rel((g1[n] / 65536.0).float().cpu().numpy(), g0[n].float().cpu().numpy())
+        assert r <= 1e-2 or err <= 1e-6, (n, r)
+    # and through GradScaler + the flat optimizer without a host synchronisation
+    from mtlora_b200.lora import mark_only_lora_as_trainable
+    from mtlora_b200.optim import FlatAdamW
+    quiet(mark_only_lora_as_trainable, net)
+    net.train()
+    opt = FlatAdamW([p for p in net.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.05, max_grad_norm=5.0)
+    scaler = torch.amp.GradScaler("cuda")
+    before = net.layers[0].blocks[0].attn.qkv.lora_shared_B.detach().clone()
+    for _ in range(2):
+        with torch.autocast("cuda", dtype=torch.float16):
+            st = net(img, return_stages=True)
+            loss = sum(v.float().pow(2).mean() for _, tl in st for v in tl.values())
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+        opt.zero_grad(set_to_none=True)
+    assert torch.isfinite(loss) and float(opt._state[0]) == 2.0
+    assert not torch.equal(before, net.layers[0].blocks[0].attn.qkv.lora_shared_B)
+
+
+def test_multitask_swin_drop_in(S):
+    """the reference's own MultiTaskSwin (hrnet heads, models/swin_mtl.py:138-246, unmodified)
+    wraps this backbone; one full train step as main.py:341-353 + utils.py:352-366 runs and updates the adapters; the
+    eval-mode forward matches the all-reference model on the same weights."""
+    from baseline import refload
+    if not refload.available():
+        pytest.skip("baseline/_ref not installed")
+    ref = refload.load()
+    tasks = TASKS6[:4]
+    ml = refload.mtlora_node(tasks, 16, 4, dropout=0.0)
+    cfg = refload.mtl_config(tasks, 224, ml)
+    torch.manual_seed(0)
+    rbb = quiet(ref.swin.SwinTransformerMTLoRA, img_size=224, num_classes=0, drop_path_rate=0.0, tasks=tasks, mtlora=ml)
+    rnet = quiet(ref.swin_mtl.MultiTaskSwin, rbb, cfg)
+    load_det(rnet.backbone)
+    bb = quiet(S.SwinTransformerMTLoRA, img_size=224, num_classes=0, drop_path_rate=0.0, tasks=tasks, mtlora=ml)
+    net = quiet(ref.swin_mtl.MultiTaskSwin, bb, cfg)
+    net.load_state_dict(rnet.state_dict())
+    rnet.cuda().eval()
+    net.cuda().eval()
+    img = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(5)).cuda()
+    with torch.no_grad():
+        ro = rnet(img)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            go = net(img)
+    for t in tasks:
+        assert go[t].shape == ro[t].shape == (2, refload.NUM_OUTPUT[t], 224, 224)
+        close(go[t], ro[t].cpu().numpy(), 2e-2, "head output " + t)
+    # one optimisation step exactly as the reference's loop does it
+    quiet(ref.lora.mark_only_lora_as_trainable, net.backbone, bias="none")
+    net.train()
+    crit = ref.losses.MultiTaskLoss(tasks, torch.nn.ModuleDict({t: ref.losses.get_loss(cfg.TASKS_CONFIG, t, cfg) for t in tasks}),
+                                    {t: refload.LOSS_WEIGHTS[t] for t in tasks})
+    targets = refload.synthetic_targets(tasks, 2, 224, torch.Generator().manual_seed(6), "cuda")
+    opt = torch.optim.AdamW([p for p in net.parameters() if p.requires_grad], lr=1e-3)
+    scaler = torch.amp.GradScaler("cuda")
+    a0 = net.backbone.layers[1].blocks[1].mlp.fc1.lora_tasks_A["sal"].detach().clone()
+    with torch.autocast("cuda", dtype=torch.float16):
+        loss, _ = crit(net(img), targets)
+    scaler.scale(loss).backward()
+    scaler.unscale_(opt)
+    norm = torch.nn.utils.clip_grad_norm_(net.parameters(), 5.0)
+    scaler.step(opt)
+    scaler.update()
+    assert torch.isfinite(loss) and torch.isfinite(norm)
+    assert not torch.equal(a0, net.backbone.layers[1].blocks[1].mlp.fc1.lora_tasks_A["sal"])
+
+
+@pytest.mark.parametrize("bias", ["all", "lora_only"])
+def test_mark_only_lora_bias_modes(S, bias):
+    """mark_only_lora_as_trainable bias modes (lora.py:618-630) agree with the reference's rule on the same model."""
+    from mtlora_b200.lora import mark_only_lora_as_trainable
+    net, _ = build(S, "h_t224_plus")
+    quiet(mark_only_lora_as_trainable, net, bias=bias)
+    tr = {n for n, p in net.named_parameters() if p.requires_grad}
+    base = {n for n, _ in net.named_parameters() if ("lora_" in n or "patch_embed" in n or "norm" in n
+                                                      or "downsample.reduction" in n or "relative_position_bias_table" in n)}
+    if bias == "all":
+        assert tr == base | {n for n, _ in net.named_parameters() if "bias" in n}
+        # the now-trainable dense biases receive gradients through the fused path
+        load_det(net)
+        net.cuda().eval()
+        img = detgen.uniform("bias.img", (1, 3, 224, 224), -2.0, 2.0).cuda()
+        st = net(img, return_stages=True)
+        sum(v.float().pow(2).mean() for _, tl in st for v in tl.values()).backward()
+        b = net.layers[0].blocks[1].mlp.fc1.linear.bias
+        assert b.grad is not None and torch.isfinite(b.grad).all() and float(b.grad.abs().max()) > 0
+    else:
+        assert tr == base          # MTLoRALinear keeps its bias inside `.linear`: the reference's rule matches nothing
+
+
+def test_dropout_mask_statistics(S):
+    """The counter-based LoRA-dropout mask shared by every kernel (lora.py:258): keep-rate within 4 sigma for several
+    (p, seed), independence across seeds and between neighbouring elements, forward/backward identity."""
+    from mtlora_b200 import ops
+    n = 1 << 22
+    ones = torch.ones(n, dtype=torch.bfloat16, device="cuda")
+    masks = {}
+    for p in (0.05, 0.1, 0.5):
+        for seed in (1, 2, 12345678901234):
+            y = ops.dropout(ones, p, seed)
+            keep = (y != 0)
+            masks[(p, seed)] = keep
+            rate = keep.float().mean().item()
+            sigma = (p * (1 - p) / n) ** 0.5
+            assert abs(rate - (1 - p)) < 4 * sigma + 2 ** -16, (p, seed, rate)       # 16-bit threshold resolution
+            kept = y[keep].float()
+            assert torch.allclose(kept, torch.full_like(kept, 1 / (1 - p)), rtol=4e-3)   # inverted-dropout scale (bf16)
+            assert torch.equal(y, ops.dropout(ones, p, seed))                             # backward re-derives it
+            # neighbouring elements (the two halves of one 32-bit hash) are uncorrelated
+            a, b = keep[0::2].float(), keep[1::2].float()
+            cov = ((a - a.mean()) * (b - b.mean())).mean().item()
+            assert abs(cov) < 5 * p * (1 - p) / (n / 2) ** 0.5, (p, seed, cov)
+    for p in (0.05, 0.5):
+        a, b = masks[(p, 1)].float(), masks[(p, 2)].float()
+        cov = ((a - a.mean()) * (b - b.mean())).mean().item()
+        assert abs(cov) < 5 * p * (1 - p) / n ** 0.5, (p, cov)
+
+
+def test_drop_path_draws(S):
+    """DropPath (timm semantics, :389-392, :398-408): independent Bernoulli(keep) / keep draws per sample, per stream and
+    per residual branch; identity in eval mode."""
+    ranks1 = [{"shared": 8, "normals": 4, "semseg": 4}]
+    blk = quiet(S.SwinTransformerBlock, dim=96, input_resolution=(14, 14), num_heads=3, window_size=7, shift_size=0,
+                drop_path=0.2, lora=True, tasks=TASKS2, mtlora=mtlora_ns(ranks1, TASKS2), layer_idx=0).cuda()
+    blk.train()
+    torch.manual_seed(0)
+    B = 4096
+    ps1, ps2 = blk.path_scales(B, 3, torch.device("cuda"))
+    assert ps1.shape == ps2.shape == (3, B)
+    allv = torch.stack([ps1, ps2]).reshape(6, B)
+    assert set(torch.unique(allv).tolist()) <= {0.0, 1.25}
+    keep = (allv != 0).float()
+    sigma = (0.2 * 0.8 / B) ** 0.5
+    assert (keep.mean(1) - 0.8).abs().max().item() < 4 * sigma
+    c = torch.corrcoef(keep)
+    off = c - torch.eye(6, device=c.device)
+    assert off.abs().max().item() < 5 / B ** 0.5          # the six (branch, stream) draws are independent
+    blk.eval()
+    assert blk.path_scales(8, 3, torch.device("cuda")) == (None, None)

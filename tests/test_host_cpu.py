@@ -97,8 +97,24 @@ def test_cpu_inputs_raise_loudly():
 
 def test_unsupported_modes_raise():
     from mtlora_b200.lora import MTLoRALinear
-    with pytest.raises(NotImplementedError):
-        MTLoRALinear(8, 8, r={"shared": 4, "a": 4}, tasks=["a"], lora_task_scale={"a": 1.0}, shared_mode="addition")
+    # 'addition' (lora.py:275-282): task adapters + the layer's own LayerNorm, no shared adapter; same surface as the
+    # reference (checked name by name against its golden parameter list in tests/test_headline_gpu.py)
+    ad = MTLoRALinear(8, 8, r={"shared": 4, "a": 4}, tasks=["a"], lora_task_scale={"a": 1.0}, shared_mode="add")
+    assert ad.shared_mode == "addition" and not hasattr(ad, "lora_shared_A")
+    assert [n for n, _ in ad.named_parameters()] == ["linear.weight", "linear.bias", "lora_tasks_A.a", "lora_tasks_B.a",
+                                                      "lora_norm.weight", "lora_norm.bias"]
+    assert ad.engine.addition and ad.engine.params() == [ad.linear.weight, ad.linear.bias, ad.lora_tasks_A["a"],
+                                                          ad.lora_tasks_B["a"]]
+    # merge(): layers without task adapters fold the shared update into W
+    mg = MTLoRALinear(8, 8, r=4, lora_shared_scale=2.0)
+    torch.nn.init.normal_(mg.lora_shared_B)
+    w0 = mg.linear.weight.detach().clone()
+    assert mg.can_merge() and mg.merge() and mg.merged and not mg.merge()
+    assert torch.allclose(mg.linear.weight, w0 + 2.0 * mg.lora_shared_B @ mg.lora_shared_A)
+    assert mg.engine.spec.r_shared == 0 and mg.engine is not mg._engine
+    mg.train()
+    assert not mg.merged and torch.allclose(mg.linear.weight, w0, atol=1e-6) and mg.engine is mg._engine
+    assert not MTLoRALinear(8, 8, r={"shared": 4, "a": 4}, tasks=["a"], lora_task_scale={"a": 1.0}).can_merge()
     ts = MTLoRALinear(8, 8, r={"shared": 4, "a": 4}, tasks=["a"], lora_task_scale=2.5, lora_shared_scale=4.0,
                       trainable_scale_shared=True, trainable_scale_per_task=True)
     # same registration order as the reference (direct parameters first, then linear, the task dicts, the scale dict)

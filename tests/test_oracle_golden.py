@@ -177,3 +177,87 @@ def test_backbone_config1(golden):
             close(sample(v.grad, 53)[3:], golden[key][3:], rtol=1e-3)
             checked += 1
     assert checked > 150
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# tests/golden/headline_vectors.npz: the configurations the headline numbers are quoted on, 'addition' mode,
+# INTERMEDIATE_SPECIALIZATION and MTLoRA+ (make_golden.headline)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,K,N,r,xt", [("lin_add_tasks", 96, 96, {"shared": 16, "normals": 4, "semseg": 4}, False),
+                                          ("lin_add_xtasks", 96, 384, {"shared": 16, "normals": 4, "semseg": 8}, True)])
+def test_mtlora_linear_addition(headline, tag, K, N, r, xt):
+    """shared_mode='addition' (lora.py:275-282): no shared adapter; shared output = pretrained + LayerNorm(sum of the task
+    outputs) with the layer's own `lora_norm` (:217-219)."""
+    shapes = {"linear.weight": (N, K), "linear.bias": (N,)}
+    for t in TASKS:
+        shapes["lora_tasks_A." + t], shapes["lora_tasks_B." + t] = (r[t], K), (N, r[t])
+    shapes["lora_norm.weight"], shapes["lora_norm.bias"] = (N,), (N,)
+    assert sorted(shapes) == sorted(headline[tag + "/param_names"].tolist())
+    p = det_module_params(tag, shapes)
+    x = detgen.uniform(tag + ".x", (2, 49, K)).requires_grad_()
+    x_tasks = {t: detgen.uniform(f"{tag}.x.{t}", (2, 49, K)).requires_grad_() for t in TASKS} if xt else None
+    y, yt = O.mtlora_linear(p, "", x, x_tasks, TASKS, 4.0, TSCALE, mode="addition")
+    loss = (y * detgen.uniform(tag + ".gy", tuple(y.shape))).sum()
+    for t in TASKS:
+        loss = loss + (yt[t] * detgen.uniform(f"{tag}.gy.{t}", tuple(y.shape))).sum()
+    loss.backward()
+    close(y, headline[tag + "/y"])
+    for t in TASKS:
+        close(yt[t], headline[f"{tag}/y.{t}"])
+    close(x.grad, headline[tag + "/dx"], rtol=5e-5)
+    if xt:
+        for t in TASKS:
+            close(x_tasks[t].grad, headline[f"{tag}/dx.{t}"], rtol=5e-5)
+    for n, v in p.items():
+        if "lora" in n:
+            close(v.grad, headline[f"{tag}/d.{n}"], rtol=1e-4)
+
+
+HEADLINE_TASKS6 = ["semseg", "normals", "sal", "human_parts", "depth", "edge"]
+HEADLINE_CASES = {   # mirrors tests/golden/make_golden.py::HEADLINE_CASES
+    "h_t448": dict(img=448, embed_dim=96, depths=(2, 2, 6, 2), heads=(3, 6, 12, 24), n_tasks=4, r_s=64, r_t=4, B=1),
+    "h_s448": dict(img=448, embed_dim=96, depths=(2, 2, 18, 2), heads=(3, 6, 12, 24), n_tasks=4, r_s=64, r_t=4, B=1),
+    "h_b448": dict(img=448, embed_dim=128, depths=(2, 2, 18, 2), heads=(4, 8, 16, 32), n_tasks=6, r_s=32, r_t=4, B=1),
+    "h_t224_r64all": dict(img=224, embed_dim=96, depths=(2, 2, 6, 2), heads=(3, 6, 12, 24), n_tasks=4, r_s=64, r_t=64, B=2),
+    "h_t224_interm": dict(img=224, embed_dim=96, depths=(2, 2, 2, 2), heads=(3, 6, 12, 24), n_tasks=2, r_s=16, r_t=4, B=2,
+                          interm=True),
+    "h_t224_plus": dict(img=224, embed_dim=96, depths=(2, 2, 2, 2), heads=(3, 6, 12, 24), n_tasks=2, r_s=16, r_t=4, B=2,
+                        downsampler=True),
+}
+
+
+# the two 18-block 448 cases take ~20 s each on 8 cores; they run on the GPU against the same vectors instead
+@pytest.mark.parametrize("case", ["h_t448", "h_t224_r64all", "h_t224_interm", "h_t224_plus"])
+def test_backbone_headline(headline, case):
+    """The oracle on the configurations the numbers are quoted on (BASELINE.json configs[1], [4]) and on the
+    INTERMEDIATE_SPECIALIZATION / MTLoRA+ variants, against the unmodified reference's own outputs and gradients."""
+    c = HEADLINE_CASES[case]
+    tasks = HEADLINE_TASKS6[:c["n_tasks"]]
+    cfg = O.OracleConfig(img_size=c["img"], embed_dim=c["embed_dim"], depths=c["depths"], num_heads=c["heads"],
+                         tasks=tuple(tasks), intermediate_specialization=c.get("interm", False))
+    ranks = [dict({"shared": c["r_s"]}, **{t: c["r_t"] for t in tasks})] * 4
+    shapes = detgen.backbone_param_shapes(cfg, ranks, downsampler_lora=c.get("downsampler", False),
+                                          intermediate_specialization=c.get("interm", False))
+    p = {k: v.requires_grad_() for k, v in detgen.make_params(shapes).items()}
+    img = detgen.uniform(case + ".img", (c["B"], 3, c["img"], c["img"]), -2.0, 2.0)
+    stages = O.backbone(p, img, cfg)
+    loss = O.backbone_loss(stages)
+    loss.backward()
+    g0 = headline[f"{case}/loss"][0]
+    assert abs(loss.item() - g0) <= 1e-4 * abs(g0)
+    for s, (xs, tl) in enumerate(stages):
+        for name, t in [(f"{case}/stage{s}.x", xs)] + [(f"{case}/stage{s}.{k}", tl[k]) for k in tasks]:
+            f = t.detach().reshape(-1).double()
+            stat = headline[name + ".stat"]
+            assert stat[2] == f.numel()
+            close(f[::101], headline[name], rtol=3e-4)
+            assert abs(f.abs().sum().item() - stat[1]) <= 1e-4 * stat[1]
+    none = sorted(n for n, v in p.items() if v.grad is None)
+    assert none == sorted(headline[f"{case}/none_grads"].tolist())
+    checked = 0
+    for n, v in p.items():
+        key = f"{case}/d.{n}"
+        if key in headline.files:
+            close(v.grad.reshape(-1)[::53], headline[key], rtol=2e-3, atol=1e-7)
+            checked += 1
+    assert checked > 150
