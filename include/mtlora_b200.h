@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MTL_ABI_VERSION 1
+#define MTL_ABI_VERSION 2
 #define MTL_MAX_TASKS 7
 
 typedef void* mtl_stream_t; /* cudaStream_t */
@@ -63,6 +63,9 @@ typedef struct mtl_linear_cfg {
   int32_t dy_has_sum;     /* mtl_linear_bwd_input, layers with task streams: dy holds 1+T+1 streams, the last one being
                            * sum_j dy[j] (mtl_scale_rows_sum) — the frozen product then reads ONE stream per column
                            * chunk instead of re-summing the 1+T streams on the tensor cores */
+  int32_t u_precomputed;  /* mtl_linear_fwd / mtl_linear_bwd_input on a layer WITHOUT task adapters: the rank-space
+                           * activations (u_save resp. g_save) are an INPUT, produced by mtl_linear_rank_project; the
+                           * kernel then runs as one dense product over the concatenated contraction [x | U].[W | B]^T */
 } mtl_linear_cfg;
 
 /* Width R of the packed rank space: every adapter (shared first, then the tasks in module order) starts on a
@@ -78,6 +81,15 @@ int mtl_linear_rank_offset(const mtl_linear_cfg* cfg, int idx);
 int mtl_linear_pack(const mtl_linear_cfg* cfg, const float* a_shared, const float* b_shared,
                     const float* const* a_tasks, const float* const* b_tasks, void* a_cat, void* b_cat,
                     void* a_cat_t, void* b_cat_t, mtl_stream_t stream);
+
+/* Rank-space projection of a layer without task adapters (lora.py:260: the `x @ A^T` half of the shared update) as a
+ * launch of its own, for the compute-bound layers of stages 2-3:
+ *   pass 0 (forward) : u[M, R] = s_sh * x[drop stream] . a_cat^T     x: [1 (+1 if dropout_p > 0), M, K], down = a_cat [R, K]
+ *   pass 1 (backward): g[M, R] = s_sh * dy . b_cat_t^T               x: dy [1, M, N],                   down = b_cat_t [R, N]
+ * The result is what mtl_linear_fwd would save as u_save (mtl_linear_bwd_input: g_save); hand it back to those calls
+ * with cfg.u_precomputed = 1. */
+int mtl_linear_rank_project(const mtl_linear_cfg* cfg, int32_t pass, const void* x, const void* down, void* u_out,
+                            mtl_stream_t stream);
 
 /* fp32 [rows, cols] -> bf16 copy (w_bf16, may be NULL) and bf16 transpose [cols, rows] (wt_bf16, may be NULL);
  * used once per frozen nn.Linear weight (lora.py:194). */
@@ -255,8 +267,9 @@ int mtl_opt_seg_size(void);
 /* out_sq[0] = sum of squares of every gradient in the table (inf / nan propagate). */
 int mtl_opt_sqnorm(const mtl_opt_seg* segs, const int32_t* prefix, int32_t n_segs, int32_t n_chunks, float* out_sq,
                    mtl_stream_t stream);
-/* One AdamW (adam_w = 1) / Adam-with-L2 (adam_w = 0) step. state: device float[4] = {steps taken, scratch, total grad
- * norm of this step (when sqnorm given), unused}, zero-initialised by the caller and owned by the optimizer.
+/* One AdamW (adam_w = 1) / Adam-with-L2 (adam_w = 0) step. state: device float[2 + n_segs] = {scratch, total grad
+ * norm of this step (when sqnorm given), steps taken by segment 0, 1, ...} (one step counter per tensor, like
+ * torch.optim: a tensor without a gradient does not advance), zero-initialised by the caller, owned by the optimizer.
  * grad_scale / found_inf: the GradScaler's device scalars or NULL (torch.amp contract of fused optimizers: gradients
  * are divided by *grad_scale, the whole step — including the step counter — is skipped when *found_inf != 0).
  * sqnorm: result of mtl_opt_sqnorm on the same (still scaled) gradients, needed when max_norm > 0:

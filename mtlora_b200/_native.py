@@ -7,7 +7,7 @@ import ctypes
 import os
 
 MTL_MAX_TASKS = 7
-MTL_ABI_VERSION = 1
+MTL_ABI_VERSION = 2
 MTL_MODE_MATRIX, MTL_MODE_MATRIXV2 = 0, 1
 MTL_ACT_NONE, MTL_ACT_GELU, MTL_ACT_GELU_GRAD = 0, 1, 2
 
@@ -36,6 +36,7 @@ class LinearCfg(ctypes.Structure):
         ("rows_per_sample", c_int32),
         ("gelu_aux_is_grad", c_int32),
         ("dy_has_sum", c_int32),
+        ("u_precomputed", c_int32),
     ]
 
 
@@ -71,6 +72,7 @@ SIGNATURES = {
     "mtl_linear_rank_offset": (c_int, [_CFG_P, c_int]),
     "mtl_linear_pack": (c_int, [_CFG_P, c_void_p, c_void_p, _PP, _PP, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mtl_cast_transpose": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "mtl_linear_rank_project": (c_int, [_CFG_P, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mtl_linear_fwd": (c_int, [_CFG_P, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
                                c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "mtl_linear_bwd_input": (c_int, [_CFG_P, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

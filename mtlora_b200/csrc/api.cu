@@ -186,6 +186,33 @@ int mtl_linear_pack(const mtl_linear_cfg* cfg, const float* a_shared, const floa
                               a_cat_t, b_cat_t, S(stream));
 }
 
+int mtl_linear_rank_project(const mtl_linear_cfg* cfg, int32_t pass, const void* x, const void* down, void* u_out,
+                            mtl_stream_t stream) {
+  RankLayout L;
+  if (int e = build_layout(cfg, &L)) return e;
+  MTL_REQUIRE(L.n == 1, "linear_rank_project: needs a layer with a shared adapter and no task adapters");
+  MTL_REQUIRE(pass == 0 || pass == 1, "linear_rank_project: pass %d (0 = forward, 1 = input gradient)", pass);
+  if (int e = check_ptr16(x, "linear_rank_project: x")) return e;
+  if (int e = check_ptr16(down, "linear_rank_project: down")) return e;
+  if (int e = check_ptr16(u_out, "linear_rank_project: u_out")) return e;
+  MTL_REQUIRE(cfg->M > 0 && cfg->M < (1ll << 31), "linear_rank_project: M=%lld out of range", (long long)cfg->M);
+  const bool drop = pass == 0 && cfg->dropout_p > 0.f;
+  LinPlan p;
+  memset(&p, 0, sizeof(p));
+  p.M = static_cast<int>(cfg->M);
+  p.Kc = pass == 0 ? cfg->in_features : cfg->out_features;
+  p.Nn = L.R_pad;
+  p.S_in = drop ? 2 : 1;
+  p.S_out = 1;
+  p.n_main = 1;
+  p.main_in[0] = drop ? 1 : 0;   // forward: the adapters read D(x[0]), appended as the last stream (lora.py:258)
+  p.out_useP[0] = 1;
+  p.ep_mode = LIN_EP_NONE;
+  p.y = static_cast<__nv_bfloat16*>(u_out);
+  p.out_scale = L.scale[0];
+  return run_linear(p, x, down, nullptr, nullptr, S(stream));
+}
+
 int mtl_cast_transpose(const float* w, void* w_bf16, void* wt_bf16, int32_t rows, int32_t cols, mtl_stream_t stream) {
   MTL_REQUIRE(w != nullptr, "cast_transpose: source is NULL");
   return launch_cast_transpose(w, w_bf16, wt_bf16, rows, cols, S(stream));
@@ -268,6 +295,10 @@ int mtl_linear_fwd(const mtl_linear_cfg* cfg, const void* x, const void* w_bf16,
     p.n_samples = static_cast<int>(cfg->M / cfg->rows_per_sample);
   }
   p.u_save = static_cast<__nv_bfloat16*>(u_save);
+  if (cfg->u_precomputed && lora) {
+    MTL_REQUIRE(L.n == 1 && u_save != nullptr, "linear_fwd: u_precomputed needs a layer without task adapters and U");
+    p.u_in = 1;
+  }
   if (drop && act != MTL_ACT_NONE) p.drop_mode = 1;
   p.drop_p = cfg->dropout_p;
   p.drop_seed = cfg->dropout_seed;
@@ -357,6 +388,10 @@ int mtl_linear_bwd_input(const mtl_linear_cfg* cfg, const void* dy, const void* 
     p.n_samples = static_cast<int>(cfg->M / cfg->rows_per_sample);
   }
   p.u_save = static_cast<__nv_bfloat16*>(g_save);
+  if (cfg->u_precomputed && lora) {
+    MTL_REQUIRE(L.n == 1 && g_save != nullptr, "linear_bwd_input: u_precomputed needs a layer without task adapters and G");
+    p.u_in = 1;
+  }
   if (drop) {
     p.drop_mode = 2;
     p.force_split = 1;

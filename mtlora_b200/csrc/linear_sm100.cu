@@ -274,7 +274,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const uint32_t stage_bytes = kTileABytes + p.stage_b_bytes;
-  const SmemLayout L = smem_layout(p.n_stages, stage_bytes, p.R_pad, p.n_slabs);
+  const SmemLayout L = smem_layout(p.n_stages, stage_bytes, p.u_in ? 0 : p.R_pad, p.n_slabs);
   const uint32_t usm_base = smem_base + L.usm;
   const uint32_t bar_base = smem_base + L.bars;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -363,8 +363,8 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             const int c0 = (it.split + ci * p.n_splits) * p.BN;
             for (int hcol = c0; hcol < c0 + p.BN && hcol < p.Nn; hcol += 64) tma_prefetch_l2_3d(&tm_pf, hcol, it.m0, sj);
           }
-        // phase 1: rank-space ("down") products
-        for (int g = 0; g < p.n_groups; ++g) {
+        // phase 1: rank-space ("down") products (u_in: U was produced by an earlier launch)
+        for (int g = 0; g < (p.u_in ? 0 : p.n_groups); ++g) {
           const int len = p.grp_len[g];
           for (int kb = 0; kb < n_kb; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u, p.wait_hint_ns);
@@ -397,10 +397,12 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           for (int a0 = 0; a0 < n_uatoms; a0 += p.up_pack) {
             mbar_wait(empty_bar(stage), phase ^ 1u, p.wait_hint_ns);
             const int na = n_uatoms - a0 < p.up_pack ? n_uatoms - a0 : p.up_pack;
-            mbar_arrive_expect_tx(full_bar(stage), na * p.BN * 128);
+            mbar_arrive_expect_tx(full_bar(stage), na * p.BN * 128 + (p.u_in ? kTileABytes : 0));
             for (int i = 0; i < na; ++i)
               tma_load_2d(up_tile_addr(smem_base + stage * stage_bytes, i, p.BN), &tm_up, full_bar(stage), (a0 + i) * 64,
                           c * p.BN);
+            // u_in (up_pack == 1): the [128 x 64] U atom of this rank block rides in the A half of the same stage
+            if (p.u_in) tma_load_2d(smem_base + stage * stage_bytes, &tm_u, full_bar(stage), a0 * 64, it.m0);
             advance();
           }
         }
@@ -426,7 +428,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         tr.ev(1000000ull + w);
         // ---- phase 1: U[:, group] = X[in] . Down[group]^T (the U columns were drained before u_ready of the
         //      previous work item, which this thread has already waited for)
-        for (int g = 0; g < p.n_groups; ++g) {
+        for (int g = 0; g < (p.u_in ? 0 : p.n_groups); ++g) {
           const uint32_t idesc = umma_idesc_bf16_m128(p.grp_len[g]);
           const uint32_t d_tmem = tmem_base + p.grp_r0[g];
           for (int kb = 0; kb < n_kb; ++kb) {
@@ -443,8 +445,8 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             advance();
           }
         }
-        if (p.R_pad > 0) umma_commit(u_full);
-        bool u_waited = (p.R_pad == 0);
+        if (p.R_pad > 0 && !p.u_in) umma_commit(u_full);
+        bool u_waited = (p.R_pad == 0) || p.u_in;
 
         for (int ci = 0; ci < it.n_my_chunks; ++ci) {
           const int c = it.split + ci * p.n_splits;
@@ -490,14 +492,16 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               u_waited = true;
             }
             // the Up tiles of all rank atoms of this chunk occupy n_up_stages consecutive ring stages
-            uint32_t up_addr[kMaxUAtoms];
+            uint32_t up_addr[kMaxUAtoms], ua_addr[kMaxUAtoms];
             {
               int s = stage;
               uint32_t ph = phase;
               for (int a0 = 0; a0 < n_uatoms; a0 += p.up_pack) {
                 mbar_wait(full_bar(s), ph, p.wait_hint_ns);
-                for (int i = 0; i < p.up_pack && a0 + i < n_uatoms; ++i)
+                for (int i = 0; i < p.up_pack && a0 + i < n_uatoms; ++i) {
                   up_addr[a0 + i] = up_tile_addr(smem_base + s * stage_bytes, i, p.BN);
+                  ua_addr[a0 + i] = p.u_in ? smem_base + s * stage_bytes : usm_base + (a0 + i) * kTileABytes;
+                }
                 if (++s == p.n_stages) {
                   s = 0;
                   ph ^= 1u;
@@ -532,7 +536,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 started = !first;
               }
               for (int a = 0; a < n_uatoms; ++a) {
-                const uint64_t adesc = umma_desc_sw128(usm_base + a * kTileABytes);
+                const uint64_t adesc = umma_desc_sw128(ua_addr[a]);
                 const uint64_t bdesc = umma_desc_sw128(up_addr[a]);
                 for (int q = 0; q < 4; ++q) {
                   const int col = a * 64 + q * 16;
@@ -560,7 +564,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             ++G;
           }
         }
-        if (p.R_pad > 0) umma_commit(usm_free);
+        if (p.R_pad > 0 && !p.u_in) umma_commit(usm_free);
       }
     }
     __syncwarp();
@@ -585,7 +589,8 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const bool is_t0 = (warp == 4 && lane == 0);
     const uint32_t thr = dropout_threshold(p.drop_p);
     const float keep_scale = 1.f / (1.f - p.drop_p);
-    const size_t stream_stride = static_cast<size_t>(p.M) * p.Nn;
+    const float out_scale = p.out_scale != 0.f ? p.out_scale : 1.f;
+    const bool scale_rows = p.rowscale_out != nullptr || out_scale != 1.f;
     constexpr bool dual = EP == LIN_EP_GELU_DUAL || EP == LIN_EP_GELU_DUAL_GRAD;
 
     uint32_t lw = 0, Cn = 0, G = 0;
@@ -599,7 +604,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const int sample = (p.rows_per_sample > 0) ? min(grow / p.rows_per_sample, p.n_samples - 1) : 0;
       const int row0 = it.m0 + q4 * 32;
 
-      if (p.R_pad > 0) {
+      if (p.R_pad > 0 && !p.u_in) {
         if (warp == 4) {   // one warp polls, the other epilogue warps block on the named barrier (no issue slots)
           mbar_wait(u_full, lw & 1u, p.wait_hint_ns);
           if (lw > 0) mbar_wait(usm_free, (lw - 1) & 1u, p.wait_hint_ns);  // previous item's delta MMAs finished reading usm
@@ -690,7 +695,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           const uint32_t acc_d = t_lane + d_col0 + (p.d_shared ? 0u : (grp * p.n_dbuf + dbuf) * p.BN);
           const uint32_t acc_p = t_lane + p_col0 + pb * p.BN;
           const bool mask_delta = multi && (p.drop_mode == 2) && j == 0;
-          const float rs = (p.rowscale_out != nullptr) ? p.rowscale_out[j * p.n_samples + sample] : 1.f;
+          const float rs = ((p.rowscale_out != nullptr) ? p.rowscale_out[j * p.n_samples + sample] : 1.f) * out_scale;
           const int n_half = (n_eff + 63) >> 6;
           for (int h = 0; h < n_half; ++h) {
             const int col_h = c * p.BN + h * 64;
@@ -770,7 +775,7 @@ mtl_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                   v2[2 * i + 1] = add2(v2[2 * i + 1], pack2(bv[i].z, bv[i].w));
                 }
               }
-              if (p.rowscale_out != nullptr) {
+              if (scale_rows) {
                 const uint64_t rs2 = pack2(rs, rs);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v2[i] = mul2(v2[i], rs2);
@@ -944,7 +949,12 @@ int plan_linear(LinPlan& p, int n_sm, uint32_t* smem_bytes_out) {
   // ---- TMEM plan -------------------------------------------------------------------------------
   // merged : one accumulator per item (dense + adapters), double-buffered between the two epilogue groups
   // multi  : dense accumulator P per chunk (n_pbuf buffers) + per-stream delta accumulators D[2]
-  const int u_cols = round_up(p.R_pad, 32);
+  if (p.u_in) {
+    MTL_REQUIRE(p.R_pad > 0 && p.R_pad <= 128 && p.u_save != nullptr, "linear: u_in needs a rank space of 16..128 columns and U");
+    MTL_REQUIRE(p.S_out == 1, "linear: u_in serves single-output-stream layers");
+  }
+  const int u_cols = p.u_in ? 0 : round_up(p.R_pad, 32);   // u_in: no rank-space accumulators in TMEM
+  const int r_smem = p.u_in ? 0 : p.R_pad;                 // ... and no U operand region in shared memory
   const bool multi = p.R_pad > 0 && (p.S_out > 1 || p.force_split || p.drop_mode == 2);
   p.n_regions = multi ? 1 + p.S_out : 1;
   // Column-chunk width BN and accumulator buffering. Short contractions (K_eff < 256: stages 0-1) are epilogue / HBM
@@ -962,7 +972,7 @@ int plan_linear(LinPlan& p, int n_sm, uint32_t* smem_bytes_out) {
   const bool ep_aux = p.ep_mode == LIN_EP_GELU_BWD || p.ep_mode == LIN_EP_MUL_AUX;
   const int want_slabs = (ep_dual || ep_aux || p.res != nullptr) ? 3 : 2;
   auto fits_smem = [&](int bn_, int slabs) {   // with the minimum ring depth
-    return smem_layout(min_stages, kTileABytes + bn_ * 128, p.R_pad, slabs).total + 1024 <= 227u * 1024;
+    return smem_layout(min_stages, kTileABytes + bn_ * 128, r_smem, slabs).total + 1024 <= 227u * 1024;
   };
   p.n_pbuf = 0;
   p.n_dbuf = 1;
@@ -1043,11 +1053,11 @@ int plan_linear(LinPlan& p, int n_sm, uint32_t* smem_bytes_out) {
   // to the store slabs. Pack the tiles — the A half of those stages is free — and, if still short, stream with one
   // spare stage instead of two.
   p.up_pack = 1;
-  if (n_uatoms > 0 && smem_layout(min_stages, stage_bytes, p.R_pad, 2).total + 1024 > 227u * 1024) {
+  if (n_uatoms > 0 && smem_layout(min_stages, stage_bytes, r_smem, 2).total + 1024 > 227u * 1024) {
     p.up_pack = 1 + kTileABytes / (bn * 128);
     const int up_stages = (n_uatoms + p.up_pack - 1) / p.up_pack;
     min_stages = up_stages + 2;
-    if (smem_layout(min_stages, stage_bytes, p.R_pad, 2).total + 1024 > 227u * 1024) min_stages = up_stages + 1;
+    if (smem_layout(min_stages, stage_bytes, r_smem, 2).total + 1024 > 227u * 1024) min_stages = up_stages + 1;
   }
 
   // ---- work decomposition: (128-row tile, column split), persistent CTAs ---------------------------------------
@@ -1079,12 +1089,13 @@ int plan_linear(LinPlan& p, int n_sm, uint32_t* smem_bytes_out) {
   // ---- shared memory: store slabs + U operand + as many ring stages as fit ---------------------------------------
   const bool has_in = ep_aux || p.res != nullptr;   // epilogue inputs staged through the slabs
   p.n_slabs = (ep_dual || has_in) ? 3 : 2;   // reduced to 2 below when smem is short
-  if (smem_layout(min_stages, stage_bytes, p.R_pad, p.n_slabs).total + 1024 > 227u * 1024) p.n_slabs = 2;
+  if (smem_layout(min_stages, stage_bytes, r_smem, p.n_slabs).total + 1024 > 227u * 1024) p.n_slabs = 2;
   p.n_stages = kMaxStages;
   while (p.n_stages > min_stages &&
-         smem_layout(p.n_stages, stage_bytes, p.R_pad, p.n_slabs).total + 1024 > 227u * 1024)
+         smem_layout(p.n_stages, stage_bytes, r_smem, p.n_slabs).total + 1024 > 227u * 1024)
     --p.n_stages;
-  const uint32_t smem_bytes = smem_layout(p.n_stages, stage_bytes, p.R_pad, p.n_slabs).total + 1024;
+  const uint32_t smem_bytes = smem_layout(p.n_stages, stage_bytes, r_smem, p.n_slabs).total + 1024;
+  MTL_REQUIRE(!p.u_in || p.up_pack == 1, "linear: u_in with packed Up tiles");
   MTL_REQUIRE(smem_bytes <= 227 * 1024, "linear: shared memory %u exceeds 227 KiB", smem_bytes);
   MTL_REQUIRE(p.ep_mode >= 0 && p.ep_mode <= 4, "linear: unknown epilogue mode %d", p.ep_mode);
   MTL_REQUIRE(!((ep_aux || ep_dual) && p.res != nullptr), "linear: GELU epilogues cannot take a residual");

@@ -84,6 +84,11 @@ struct LinPlan {
   unsigned long long* trace;  // debug timeline of CTA 0 (MTL_LINEAR_TRACE), else null: [role][1024] (time, code) pairs
   uint32_t wait_hint_ns;  // mbarrier.try_wait suspend-time hint used by every role's waits
   int force_split;  // keep dense and adapter accumulators in separate TMEM regions even if S_out == 1
+  // u_in = 1: the rank-space operand U [M, R_pad] (bf16, already scaled) was produced by an earlier launch
+  // (mtl_linear_rank_project) and lives at `u_save`: phase 1 and the TMEM -> smem conversion are skipped, the U atoms
+  // travel through the TMA ring next to the Up tiles like one more k-block of the contraction. Single-adapter layers.
+  int u_in;
+  float out_scale;  // multiplies the accumulator (+ bias) before the residual; 0 is read as 1
 };
 
 // TMA descriptor of a bf16 row-major [d2][d1][d0] tensor (d0 contiguous, `pitch` elements between rows, 0 = dense),

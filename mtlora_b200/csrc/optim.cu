@@ -71,15 +71,16 @@ opt_adamw_kernel(const mtl_opt_seg* __restrict__ segs, const int32_t* __restrict
                  float* __restrict__ flat_m, float* __restrict__ flat_v, float* __restrict__ state,
                  const float* __restrict__ grad_scale, const float* __restrict__ found_inf,
                  const float* __restrict__ sqnorm, const __grid_constant__ StepArgs a) {
-  // state[0] = number of optimizer steps taken so far, state[1] = CTA completion counter of this launch,
-  // state[2] = total gradient norm of this step (after unscaling, before clipping; reported to the caller)
+  // state[0] = CTA completion counter of this launch, state[1] = total gradient norm of this step (after unscaling,
+  // before clipping; reported to the caller), state[2 + i] = number of steps taken by segment i (torch.optim keeps one
+  // step counter per parameter: a parameter without a gradient does not advance)
   const bool skip = found_inf != nullptr && *found_inf != 0.f;
-  const float step_prev = state[0];
   const int c = blockIdx.x;
   if (!skip) {
     const int s = find_seg(prefix, n_segs, c);
     const mtl_opt_seg sg = segs[s];
     if (sg.grad != nullptr) {
+      const float step_prev = state[2 + s];
       const mtl_opt_group g = a.groups[sg.group];
       const float inv_scale = grad_scale != nullptr ? 1.f / *grad_scale : 1.f;
       float coef = inv_scale;
@@ -110,15 +111,22 @@ opt_adamw_kernel(const mtl_opt_seg* __restrict__ segs, const int32_t* __restrict
       }
     }
   }
-  // the last CTA to finish advances the step counter (every CTA has read it by then) and publishes the norm
+  // the last CTA to finish advances the step counters (every CTA has read its own by then) and publishes the norm
+  __shared__ int is_last;
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    const float done = atomicAdd(state + 1, 1.f);
-    if (done == static_cast<float>(gridDim.x - 1)) {
-      state[1] = 0.f;
-      if (!skip) state[0] = step_prev + 1.f;
-      if (sqnorm != nullptr) state[2] = sqrtf(*sqnorm) * (grad_scale != nullptr ? 1.f / *grad_scale : 1.f);
+    const float done = atomicAdd(state, 1.f);
+    is_last = done == static_cast<float>(gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    if (!skip)
+      for (int i = threadIdx.x; i < n_segs; i += kThreads)
+        if (segs[i].grad != nullptr) state[2 + i] += 1.f;
+    if (threadIdx.x == 0) {
+      state[0] = 0.f;
+      if (sqnorm != nullptr) state[1] = sqrtf(*sqnorm) * (grad_scale != nullptr ? 1.f / *grad_scale : 1.f);
     }
   }
 }

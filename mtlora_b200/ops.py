@@ -6,12 +6,14 @@ task-shared stream, streams 1..T the per-task streams in module task order; para
 bf16 operand copies are produced by `pack_adapters` / `cast_transpose`; gradients come back in fp32.
 """
 import ctypes
+import os
 
 import torch
 
 from . import _native as N
 
 BF16 = torch.bfloat16
+PRE_PROJECT_MIN = int(os.environ.get("MTL_PRE_PROJECT_MIN", "256"))   # tuning aid; see LinearSpec.pre_project
 
 
 def _chk(t, dtype, name):
@@ -59,7 +61,8 @@ class LinearSpec:
         self.offsets = [lib.mtl_linear_rank_offset(ctypes.byref(c), i) for i in range(self.S_out if self.r_shared else 0)]
         self.ranks = ([self.r_shared] + self.r_tasks) if self.r_shared else []
 
-    def cfg(self, M, x_tasks_given, dropout_p=0.0, seed=0, rows_per_sample=0, gelu_aux_is_grad=False, dy_has_sum=False):
+    def cfg(self, M, x_tasks_given, dropout_p=0.0, seed=0, rows_per_sample=0, gelu_aux_is_grad=False, dy_has_sum=False,
+            u_precomputed=False):
         c = N.LinearCfg()
         c.M = int(M)
         c.in_features, c.out_features = self.K, self.Nf
@@ -76,7 +79,16 @@ class LinearSpec:
         c.rows_per_sample = int(rows_per_sample)
         c.gelu_aux_is_grad = 1 if gelu_aux_is_grad else 0
         c.dy_has_sum = 1 if dy_has_sum else 0
+        c.u_precomputed = 1 if u_precomputed else 0
         return c
+
+    def pre_project(self, M):
+        """Whether the rank-space projection runs as a launch of its own (mtl_linear_rank_project) and the main kernel as
+        one dense product over the concatenated contraction: layers without task adapters in the compute-bound regime
+        (stages 2-3: both sides >= PRE_PROJECT_MIN), where re-forming U inside every column split of a row tile costs more
+        than one extra pass over x. Below that the layers are HBM-bound and keep U on chip."""
+        return (self.r_shared > 0 and self.T == 0 and self.R_pad <= 128 and min(self.K, self.Nf) >= PRE_PROJECT_MIN
+                and M >= 128)
 
     def n_in_streams(self, x_tasks_given, dropout_p):
         has_lora = self.r_shared > 0
@@ -136,11 +148,14 @@ def linear_fwd(spec, x, w_bf16, bias, a_cat, b_cat, *, x_tasks_given=False, act_
     y = torch.empty((spec.S_out, M, spec.Nf), dtype=BF16, device=dev)
     drop = dropout_p > 0 and spec.r_shared > 0
     y_act = torch.empty((spec.S_out + (1 if drop else 0), M, spec.Nf), dtype=BF16, device=dev) if act_gelu else None
-    u = torch.empty((M, spec.R_pad), dtype=BF16, device=dev) if (save_u and spec.r_shared > 0) else None
+    pre = spec.pre_project(M)
+    u = torch.empty((M, spec.R_pad), dtype=BF16, device=dev) if ((save_u or pre) and spec.r_shared > 0) else None
     res_streams = 0
     if residual is not None:
         res_streams = residual.shape[0]
-    c = spec.cfg(M, x_tasks_given, dropout_p, seed, rows_per_sample)
+    c = spec.cfg(M, x_tasks_given, dropout_p, seed, rows_per_sample, u_precomputed=pre)
+    if pre:
+        N.call("mtl_linear_rank_project", ctypes.byref(c), 0, N.ptr(x), N.ptr(a_cat), N.ptr(u), N.stream())
     N.call("mtl_linear_fwd", ctypes.byref(c), N.ptr(x), N.ptr(w_bf16), N.ptr(bias), N.ptr(a_cat), N.ptr(b_cat),
            (N.MTL_ACT_GELU_GRAD if gelu_grad else N.MTL_ACT_GELU) if act_gelu else N.MTL_ACT_NONE, N.ptr(y), N.ptr(y_act),
            N.ptr(residual), res_streams,
@@ -161,8 +176,12 @@ def linear_bwd_input(spec, dy, wt_bf16, a_cat_t, b_cat_t, *, x_tasks_given=False
         raise ValueError(f"linear_bwd_input: dy shape {tuple(dy.shape)} does not match the layer ({spec.S_out}, M, {spec.Nf})")
     xt = x_tasks_given and spec.T > 0
     dx = torch.empty((1 + (spec.T if xt else 0), M, spec.K), dtype=BF16, device=dy.device)
-    g = torch.empty((M, spec.R_pad), dtype=BF16, device=dy.device) if (save_g and spec.r_shared > 0) else None
-    c = spec.cfg(M, x_tasks_given, dropout_p, seed, rows_per_sample, gelu_aux_is_grad=aux_is_grad, dy_has_sum=dy_has_sum)
+    pre = spec.pre_project(M) and not dy_has_sum
+    g = torch.empty((M, spec.R_pad), dtype=BF16, device=dy.device) if ((save_g or pre) and spec.r_shared > 0) else None
+    c = spec.cfg(M, x_tasks_given, dropout_p, seed, rows_per_sample, gelu_aux_is_grad=aux_is_grad, dy_has_sum=dy_has_sum,
+                 u_precomputed=pre)
+    if pre:
+        N.call("mtl_linear_rank_project", ctypes.byref(c), 1, N.ptr(dy), N.ptr(b_cat_t), N.ptr(g), N.stream())
     N.call("mtl_linear_bwd_input", ctypes.byref(c), N.ptr(dy), N.ptr(wt_bf16), N.ptr(a_cat_t), N.ptr(b_cat_t),
            N.ptr(dx), N.ptr(gelu_aux), N.ptr(path_scale), N.ptr(g), N.stream(),
            meta=("bwd_input", M, spec.K, spec.Nf, dx.shape[0], S, spec.R_pad, sum(spec.ranks), False))

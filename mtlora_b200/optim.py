@@ -65,7 +65,7 @@ class FlatAdamW(torch.optim.Optimizer):
         self._ps, self._pgroup, self._offs = ps, groups, offs
         self._m = torch.zeros(n, dtype=torch.float32, device=dev)
         self._v = torch.zeros(n, dtype=torch.float32, device=dev)
-        self._state = torch.zeros(4, dtype=torch.float32, device=dev)
+        self._state = torch.zeros(2 + len(ps), dtype=torch.float32, device=dev)   # scratch, grad norm, per-tensor steps
         self._sq = torch.zeros(1, dtype=torch.float32, device=dev)
         prefix, c = [], 0
         for p in ps:
@@ -83,7 +83,7 @@ class FlatAdamW(torch.optim.Optimizer):
         assert N.load().mtl_opt_seg_size() == ctypes.sizeof(N.OptSeg)
         # torch.optim.AdamW-shaped per-parameter state (views into the flat buffers) for state_dict() / checkpoints
         for i, p in enumerate(ps):
-            self.state[p] = {"step": self._state[0], "exp_avg": self._m[offs[i]:offs[i] + p.numel()].view_as(p),
+            self.state[p] = {"step": self._state[2 + i], "exp_avg": self._m[offs[i]:offs[i] + p.numel()].view_as(p),
                              "exp_avg_sq": self._v[offs[i]:offs[i] + p.numel()].view_as(p)}
         self._built = True
 
@@ -93,7 +93,6 @@ class FlatAdamW(torch.optim.Optimizer):
         super().load_state_dict(state_dict)
         # re-home the loaded moments into the flat buffers
         with torch.no_grad():
-            step = None
             for i, p in enumerate(self._ps):
                 st = self.state.get(p, {})
                 m = self._m[self._offs[i]:self._offs[i] + p.numel()].view_as(p)
@@ -101,14 +100,12 @@ class FlatAdamW(torch.optim.Optimizer):
                 if "exp_avg" in st:
                     m.copy_(st["exp_avg"])
                     v.copy_(st["exp_avg_sq"])
-                    step = st.get("step", step)
-                self.state[p] = {"step": self._state[0], "exp_avg": m, "exp_avg_sq": v}
-            if step is not None:
-                self._state[0] = float(step)
+                    self._state[2 + i] = float(st.get("step", 0.0))
+                self.state[p] = {"step": self._state[2 + i], "exp_avg": m, "exp_avg_sq": v}
 
     def last_grad_norm(self):
         """Total gradient norm of the last step (unscaled, before clipping) as a device scalar; needs max_grad_norm."""
-        return self._state[2]
+        return self._state[1]
 
     # ---- step --------------------------------------------------------------------------------------------------
     @torch.no_grad()

@@ -950,7 +950,9 @@ class PatchEmbed(nn.Module):
         B, C, H, W = x.shape
         assert H == self.img_size[0] and W == self.img_size[1], \
             f"Input image size ({H}*{W}) doesn't match model ({self.img_size[0]}*{self.img_size[1]})."
-        bf16_autocast = x.is_cuda and torch.is_autocast_enabled() and _autocast_cuda_dtype() == BF16
+        # any autocast dtype: the kernels compute in bf16 with fp32 accumulation (the backbone casts its stage outputs to
+        # the autocast dtype at its boundary, see _out_dtype)
+        bf16_autocast = x.is_cuda and torch.is_autocast_enabled()
         if (bf16_autocast and type(self.norm) is nn.LayerNorm and x.dtype == torch.float32 and C == 3
                 and not x.requires_grad   # the fused kernel produces no image gradient
                 and tuple(self.patch_size) == (4, 4) and self.embed_dim in (96, 128) and self.proj.bias is not None):
@@ -961,6 +963,8 @@ class PatchEmbed(nn.Module):
             y = self.proj(x.contiguous(memory_format=torch.channels_last))   # (B, C, Ph, Pw) bf16, NHWC strides
             y = y.permute(0, 2, 3, 1).contiguous()                           # no copy when the conv answered NHWC
             y = y.view(B, -1, self.embed_dim)
+            if y.dtype != BF16:
+                y = y.to(BF16)
             return _LayerNormFn.apply(y, self.norm.weight, self.norm.bias, self.norm.eps)
         x = self.proj(x).flatten(2).transpose(1, 2)  # B Ph*Pw C
         if self.norm is not None:

@@ -59,6 +59,7 @@ def test_cfg_struct_layout(lib):
     assert f.M.offset == 0 and f.in_features.offset == 8 and f.r_task.offset == 32
     assert f.dropout_seed.offset % 8 == 0 and f.rows_per_sample.offset == f.dropout_seed.offset + 8
     assert f.dy_has_sum.offset == f.gelu_aux_is_grad.offset + 4 == f.rows_per_sample.offset + 8
+    assert f.u_precomputed.offset == f.dy_has_sum.offset + 4
 
 
 def test_no_cpu_fallback():

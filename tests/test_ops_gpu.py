@@ -112,6 +112,12 @@ LINEAR_CASES = [
     ("wide_proj", 392,   96,   96,  64,  [64] * 4,     True,  False, 1,    True),
     ("wide_fc1",  40000, 96,   384, 64,  [64] * 4,     True,  True,  0,    False),
     ("wide_fc2",  3136,  1536, 384, 64,  [64] * 4,     True,  False, 5,    False),
+    # layers without task adapters in the compute-bound regime: rank-space projection as a launch of its own
+    # (mtl_linear_rank_project) + one dense product over the concatenated contraction (LinearSpec.pre_project)
+    ("s2_qkv",    1000,  384,  1152, 64, [],           False, False, 0,    False),
+    ("s2_fc1",    25088, 384,  1536, 64, [],           False, True,  0,    False),
+    ("s2_fc2",    777,   1536, 384, 64,  [],           False, False, 1,    True),
+    ("s3_r16",    640,   768,  768, 16,  [],           False, False, 1,    False),
 ]
 
 
@@ -333,6 +339,35 @@ def test_linear_dropout_stream(ops):
     da, db = ops.linear_bwd_params(spec, x, dy, u, g, dropout_p=p_drop)
     check(da[0:16], pr["lora_shared_A"].grad, tol=2e-2, what="dA shared")
     check(db[:, 16:20], pr["lora_tasks_B.t0"].grad, tol=2e-2, what="dB task0")
+
+
+@pytest.mark.parametrize("pre", [True, False])
+def test_linear_pre_project_with_dropout(ops, pre, monkeypatch):
+    """Stage-2 layer without task adapters, LoRA dropout on: the adapters read D(x) (appended stream), the frozen product
+    reads x; with and without the separate rank-projection launch (both must match the fp32 math, and each other)."""
+    monkeypatch.setattr(ops, "PRE_PROJECT_MIN", 256 if pre else 1 << 30)
+    M, K, N, p_drop, seed = 3000, 384, 1152, 0.25, 4321
+    spec, p, tasks, tscale = make_layer(ops, "prj", K, N, 64, [])
+    assert spec.pre_project(M) == pre
+    wb, wt, a_cat, b_cat, a_cat_t, b_cat_t = pack(ops, spec, p, tasks)
+    x0 = bf(dev(detgen.uniform("prj.x", (1, M, K))))
+    xd = ops.dropout(x0, p_drop, seed)
+    x = torch.cat([x0, xd]).contiguous()
+    y, _, u = ops.linear_fwd(spec, x, wb, p["linear.bias"], a_cat, b_cat, dropout_p=p_drop, seed=seed, save_u=True)
+    pr = {k: v.clone().requires_grad_() for k, v in p.items()}
+    xf = x0.float()[0].requires_grad_()
+    mask = (xd[0] != 0).float() / (1 - p_drop)
+    ref = torch.nn.functional.linear(xf, pr["linear.weight"], pr["linear.bias"]) + \
+        4.0 * ((xf * mask) @ pr["lora_shared_A"].t() @ pr["lora_shared_B"].t())
+    check(y[0], ref, what="y")
+    check(u[:, :64], 4.0 * ((xf * mask) @ pr["lora_shared_A"].t()), what="U")
+    dy = bf(dev(detgen.uniform("prj.dy", (1, M, N))))
+    (ref * dy[0].float()).sum().backward()
+    dx, g = ops.linear_bwd_input(spec, dy, wt, a_cat_t, b_cat_t, dropout_p=p_drop, seed=seed, save_g=True)
+    check(dx[0], xf.grad, what="dx")
+    da, db = ops.linear_bwd_params(spec, x, dy, u, g, dropout_p=p_drop)
+    check(da[0:64], pr["lora_shared_A"].grad, tol=2e-2, what="dA")
+    check(db[:, 0:64], pr["lora_shared_B"].grad, tol=2e-2, what="dB")
 
 
 @pytest.mark.parametrize("r_s", [4, 64, 256])

@@ -56,7 +56,10 @@ def test_flat_adamw_matches_torch(cuda, clip):
         for i, (x, y) in enumerate(zip(a, b)):
             assert torch.allclose(x, y, rtol=2e-6, atol=1e-7), (it, i, (x - y).abs().max().item())
     sd = oa.state_dict()
-    assert len(sd["state"]) == len(SHAPES) - 1                 # index 7 never had a gradient but has (zero) state
+    assert len(sd["state"]) == len(SHAPES)
+    # per-parameter step counters (state indices follow the param_groups: 7 matrices first, then the 1-D tensors):
+    # SHAPES[7] = (1,) never had a gradient, SHAPES[3] = (96, 4) skipped every other step
+    assert float(sd["state"][8]["step"]) == 0.0 and float(sd["state"][3]["step"]) == 3.0
     for k, st in sd["state"].items():
         assert set(st) == {"step", "exp_avg", "exp_avg_sq"}
 
@@ -89,7 +92,7 @@ def test_flat_adamw_grad_scaler_contract(cuda):
         assert sa.get_scale() == sb.get_scale()
         for i, (x, y) in enumerate(zip(a, b)):
             assert torch.allclose(x, y, rtol=3e-6, atol=1e-7), (it, i, (x - y).abs().max().item())
-    assert float(oa._state[0]) == 4.0            # one of the five steps was skipped
+    assert float(oa._state[2]) == 4.0            # one of the five steps was skipped
 
 
 def test_flat_adamw_state_dict_round_trip(cuda):
