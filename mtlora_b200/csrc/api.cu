@@ -197,10 +197,16 @@ int mtl_linear_rank_project(const mtl_linear_cfg* cfg, int32_t pass, const void*
   if (int e = check_ptr16(u_out, "linear_rank_project: u_out")) return e;
   MTL_REQUIRE(cfg->M > 0 && cfg->M < (1ll << 31), "linear_rank_project: M=%lld out of range", (long long)cfg->M);
   const bool drop = pass == 0 && cfg->dropout_p > 0.f;
+  const int Kc = pass == 0 ? cfg->in_features : cfg->out_features;
+  if (g_probe == nullptr && rank_project_supported(L.R_pad, Kc)) {
+    // forward: the adapters read D(x[0]), appended as the last stream (lora.py:258)
+    const __nv_bfloat16* xs = static_cast<const __nv_bfloat16*>(x) + (drop ? static_cast<size_t>(cfg->M) * Kc : 0);
+    return launch_rank_project(xs, down, u_out, static_cast<int>(cfg->M), Kc, L.R_pad, L.scale[0], S(stream));
+  }
   LinPlan p;
   memset(&p, 0, sizeof(p));
   p.M = static_cast<int>(cfg->M);
-  p.Kc = pass == 0 ? cfg->in_features : cfg->out_features;
+  p.Kc = Kc;
   p.Nn = L.R_pad;
   p.S_in = drop ? 2 : 1;
   p.S_out = 1;

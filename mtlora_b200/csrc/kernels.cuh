@@ -82,6 +82,12 @@ struct XtyJobGroup {
 int launch_xty_groups(const XtyOperand* wide, const XtyOperand* rank, const XtyJobGroup* groups, int n_groups,
                       long M, int rows_per_sample, cudaStream_t stream);
 
+// rankproj.cu -------------------------------------------------------------------------------------
+// out[M, R] = scale * X[M, K] . Down[R, K]^T (bf16, fp32 accumulation) for R in {16, 32, 64, 128}
+bool rank_project_supported(int R, int K);
+int launch_rank_project(const void* x, const void* down, void* out, int M, int K, int R, float scale,
+                        cudaStream_t stream);
+
 // optim.cu ----------------------------------------------------------------------------------------
 int opt_sqnorm(const mtl_opt_seg* segs, const int32_t* prefix, int n_segs, int n_chunks, float* out,
                cudaStream_t stream);

@@ -242,7 +242,7 @@ __device__ __forceinline__ float subwarp_sum(float v) {
 }
 
 template <int LPR, int VPT>
-__global__ void __launch_bounds__(256, 4) ln_fwd_fast_kernel(const LnFwdParams p) {
+__global__ void __launch_bounds__(256, VPT >= 6 ? 2 : 4) ln_fwd_fast_kernel(const LnFwdParams p) {
   // gamma / beta live in shared memory (broadcast 16-byte reads) and the row stays packed (bf16) in registers, so the
   // kernel fits 64 registers: 32 resident warps per SM keep ~48 KB of loads in flight (the kernel is latency-bound:
   // 16 warps x 48 B per lane measured 4.5 TB/s)
@@ -332,29 +332,38 @@ __global__ void __launch_bounds__(256, 4) ln_fwd_fast_kernel(const LnFwdParams p
   }
 }
 
+// VPT >= 6 (PatchMerging rows of 1536 / 2048 channels): gamma is read from shared memory instead of registers and one
+// CTA per SM may use the whole register file (the row and the dgamma / dbeta partial sums stay in registers)
 template <int LPR, int VPT, bool PARAM_GRADS>
-__global__ void __launch_bounds__(256, 2) ln_bwd_fast_kernel(const LnBwdParams p) {
-  extern __shared__ float red[];  // [2][C]
+__global__ void __launch_bounds__(256, VPT >= 6 ? 1 : 2) ln_bwd_fast_kernel(const LnBwdParams p) {
+  extern __shared__ float red[];  // [2][C] (+ [C] gamma when GS)
   constexpr int RPW = 32 / LPR;
+  constexpr bool GS = VPT >= 6;
+  float* sgam = red + 2 * p.C;
+  if (GS) {
+    for (int i = threadIdx.x; i < p.C; i += blockDim.x) sgam[i] = p.gamma[i];
+  }
   if (PARAM_GRADS) {
     for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) red[i] = 0.f;
-    __syncthreads();
   }
+  if (GS || PARAM_GRADS) __syncthreads();
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPR, rsel = lane / LPR;
   const long warp_g = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long n_warps = static_cast<long>(gridDim.x) * (blockDim.x >> 5);
   const int Cs = p.merge ? p.C >> 2 : p.C;
   const int vec_per_seg = Cs >> 3;
-  float gam[VPT][8];
+  float gam[GS ? 1 : VPT][8];
   float dg[PARAM_GRADS ? VPT : 1][8], db[PARAM_GRADS ? VPT : 1][8];
 #pragma unroll
   for (int k = 0; k < VPT; ++k) {
     const int v = sub + k * LPR;
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * v);
-    const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * v + 1);
-    gam[k][0] = g0.x; gam[k][1] = g0.y; gam[k][2] = g0.z; gam[k][3] = g0.w;
-    gam[k][4] = g1.x; gam[k][5] = g1.y; gam[k][6] = g1.z; gam[k][7] = g1.w;
+    if (!GS) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * v);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * v + 1);
+      gam[k][0] = g0.x; gam[k][1] = g0.y; gam[k][2] = g0.z; gam[k][3] = g0.w;
+      gam[k][4] = g1.x; gam[k][5] = g1.y; gam[k][6] = g1.z; gam[k][7] = g1.w;
+    }
     if (PARAM_GRADS) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) dg[k][e] = db[k][e] = 0.f;
@@ -388,12 +397,21 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_fast_kernel(const LnBwdParams p
 #pragma unroll
     for (int k = 0; k < VPT; ++k) {
       const uint32_t wx[4] = {qx[k].x, qx[k].y, qx[k].z, qx[k].w}, wd[4] = {qd[k].x, qd[k].y, qd[k].z, qd[k].w};
+      float gk[8];
+      if (GS) {
+        const float4 g0 = *reinterpret_cast<const float4*>(sgam + (sub + k * LPR) * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(sgam + (sub + k * LPR) * 8 + 4);
+        gk[0] = g0.x; gk[1] = g0.y; gk[2] = g0.z; gk[3] = g0.w; gk[4] = g1.x; gk[5] = g1.y; gk[6] = g1.z; gk[7] = g1.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gk[e] = gam[k][e];
+      }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float x = (e & 1) ? bf16hi_to_f32(wx[e >> 1]) : bf16lo_to_f32(wx[e >> 1]);
         const float d = (e & 1) ? bf16hi_to_f32(wd[e >> 1]) : bf16lo_to_f32(wd[e >> 1]);
         const float h = (x - mean) * rstd;
-        const float g = d * gam[k][e];
+        const float g = d * gk[e];
         s1 += g;
         s2 += g * h;
         if (PARAM_GRADS) {
@@ -413,11 +431,20 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_fast_kernel(const LnBwdParams p
         wr[0] = qr.x; wr[1] = qr.y; wr[2] = qr.z; wr[3] = qr.w;
       }
       const uint32_t wx[4] = {qx[k].x, qx[k].y, qx[k].z, qx[k].w}, wd[4] = {qd[k].x, qd[k].y, qd[k].z, qd[k].w};
+      float gk[8];
+      if (GS) {
+        const float4 g0 = *reinterpret_cast<const float4*>(sgam + (sub + k * LPR) * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(sgam + (sub + k * LPR) * 8 + 4);
+        gk[0] = g0.x; gk[1] = g0.y; gk[2] = g0.z; gk[3] = g0.w; gk[4] = g1.x; gk[5] = g1.y; gk[6] = g1.z; gk[7] = g1.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gk[e] = gam[k][e];
+      }
       uint32_t o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float h0 = (bf16lo_to_f32(wx[e]) - mean) * rstd, h1 = (bf16hi_to_f32(wx[e]) - mean) * rstd;
-        const float g0 = bf16lo_to_f32(wd[e]) * gam[k][2 * e], g1 = bf16hi_to_f32(wd[e]) * gam[k][2 * e + 1];
+        const float g0 = bf16lo_to_f32(wd[e]) * gk[2 * e], g1 = bf16hi_to_f32(wd[e]) * gk[2 * e + 1];
         o[e] = pack_bf16x2(rstd * (g0 - s1 - h0 * s2) + bf16lo_to_f32(wr[e]),
                            rstd * (g1 - s1 - h1 * s2) + bf16hi_to_f32(wr[e]));
       }
@@ -461,6 +488,8 @@ static bool ln_fast_shape(int C, int* lpr, int* vpt) {
     case 256: *lpr = 16; *vpt = 2; return true;
     case 512: *lpr = 32; *vpt = 2; return true;
     case 1024: *lpr = 32; *vpt = 4; return true;
+    case 1536: *lpr = 32; *vpt = 6; return true;   // PatchMerging of stage 2 (Swin-T/S): 4 x 384
+    case 2048: *lpr = 32; *vpt = 8; return true;   // ... Swin-B: 4 x 512
     default: return false;
   }
 }
@@ -471,7 +500,7 @@ static void ln_fwd_launch(const LnFwdParams& p, unsigned grid, cudaStream_t stre
 }
 template <int LPR, int VPT>
 static void ln_bwd_launch(const LnBwdParams& p, unsigned grid, cudaStream_t stream) {
-  const size_t sm = 2 * p.C * sizeof(float);
+  const size_t sm = (VPT >= 6 ? 3 : 2) * p.C * sizeof(float);
   if (p.dgamma) ln_bwd_fast_kernel<LPR, VPT, true><<<grid, 256, sm, stream>>>(p);
   else ln_bwd_fast_kernel<LPR, VPT, false><<<grid, 256, sm, stream>>>(p);
 }
@@ -485,6 +514,8 @@ static void ln_bwd_launch(const LnBwdParams& p, unsigned grid, cudaStream_t stre
     case 1602: FN<16, 2>(__VA_ARGS__); break;      \
     case 3202: FN<32, 2>(__VA_ARGS__); break;      \
     case 3204: FN<32, 4>(__VA_ARGS__); break;      \
+    case 3206: FN<32, 6>(__VA_ARGS__); break;      \
+    case 3208: FN<32, 8>(__VA_ARGS__); break;      \
     default: break;                                \
   }
 

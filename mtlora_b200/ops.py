@@ -16,6 +16,37 @@ BF16 = torch.bfloat16
 PRE_PROJECT_MIN = int(os.environ.get("MTL_PRE_PROJECT_MIN", "256"))   # tuning aid; see LinearSpec.pre_project
 
 
+class _ZeroArena:
+    """Zero-initialised fp32 scratch for the gradient accumulators of one backward pass (dA / dB, LayerNorm affine,
+    rel-pos tables): one cudaMemset-sized fill per 16 MB chunk instead of one fill kernel per accumulator (~100 per
+    step). Slices are views: a chunk lives as long as any gradient carved from it."""
+    CHUNK = 4 << 20   # floats
+
+    def __init__(self):
+        self.buf = {}
+
+    def take(self, n, device):
+        n_al = (n + 63) // 64 * 64          # 256-byte aligned slices
+        if n_al > self.CHUNK // 4:
+            return torch.zeros(n, dtype=torch.float32, device=device)
+        key = (device.type, device.index)
+        buf, off = self.buf.get(key, (None, 0))
+        if buf is None or off + n_al > buf.numel():
+            buf, off = torch.zeros(self.CHUNK, dtype=torch.float32, device=device), 0
+        self.buf[key] = (buf, off + n_al)
+        return buf[off:off + n]
+
+
+_arena = _ZeroArena()
+
+
+def zeros_f32(shape, device):
+    n = 1
+    for d in shape:
+        n *= int(d)
+    return _arena.take(n, device).view(*shape)
+
+
 def _chk(t, dtype, name):
     if t is None:
         return
@@ -197,7 +228,7 @@ def linear_bwd_params(spec, x, dy, u_save, g_save, *, x_tasks_given=False, x_gel
     if dy.shape[0] != spec.S_out + (1 if dy_has_sum else 0):
         raise ValueError(f"linear_bwd_params: dy has {dy.shape[0]} streams, expected {spec.S_out + (1 if dy_has_sum else 0)}")
     # one zero-fill for both accumulators
-    buf = torch.zeros(spec.R_pad * (spec.K + spec.Nf), dtype=torch.float32, device=dy.device)
+    buf = zeros_f32((spec.R_pad * (spec.K + spec.Nf),), dy.device)
     da = buf[:spec.R_pad * spec.K].view(spec.R_pad, spec.K)
     db = buf[spec.R_pad * spec.K:].view(spec.Nf, spec.R_pad)
     c = spec.cfg(M, x_tasks_given, dropout_p, 0, rows_per_sample, dy_has_sum=dy_has_sum)
@@ -213,7 +244,7 @@ def xty(p, q, alpha=1.0, out=None):
     M, a = p.shape
     b = q.shape[1]
     if out is None:
-        out = torch.zeros((a, b), dtype=torch.float32, device=p.device)
+        out = zeros_f32((a, b), p.device)
     N.call("mtl_xty", N.ptr(p), a, N.ptr(q), b, N.ptr(out), b, M, a, b, float(alpha), N.stream())
     return out
 
@@ -241,7 +272,7 @@ def window_attention_bwd(qkv, dout, rpb, lse, num_heads, window_size, shift_size
     B, H, W, C3 = qkv.shape
     C = C3 // 3
     dqkv = torch.empty_like(qkv)
-    drpb = torch.zeros_like(rpb) if want_drpb else None
+    drpb = zeros_f32(tuple(rpb.shape), rpb.device) if want_drpb else None
     N.call("mtl_window_attention_bwd", N.ptr(qkv), N.ptr(dout), N.ptr(rpb), N.ptr(mask),
            0 if mask is None else mask.shape[0], N.ptr(lse), N.ptr(dqkv), N.ptr(drpb), B, H, W, C, num_heads,
            window_size, shift_size, float(scale), N.stream())
@@ -313,7 +344,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, merge_hw=None, want_param
     rows = mean.numel()
     dx = torch.empty_like(x)
     if want_param_grads:
-        gb = torch.zeros((2, C), dtype=gamma.dtype, device=gamma.device)   # one zero-fill for both accumulators
+        gb = zeros_f32((2, C), gamma.device)
         dg, db = gb[0], gb[1]
     else:
         dg = db = None

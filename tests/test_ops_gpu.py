@@ -524,7 +524,7 @@ def test_window_process_bitwise(ops, dtype, B, H, W, C, shift, ws):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("rows,C", [(1000, 96), (777, 192), (64, 768), (300, 1536), (50, 3072)])
+@pytest.mark.parametrize("rows,C", [(1000, 96), (777, 192), (64, 768), (300, 1536), (4001, 1536), (333, 2048), (50, 3072)])
 def test_layernorm(ops, rows, C):
     x = bf(dev(detgen.uniform(f"ln.{rows}.{C}", (rows, C), -2.0, 3.0)))
     g = dev(detgen.std_uniform(f"ln.g.{C}", (C,), 0.2, 1.0))
