@@ -4,7 +4,7 @@ NVCC      ?= /usr/local/cuda/bin/nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr
 CSRC      := mtlora_b200/csrc
-OBJS      := $(CSRC)/api.o $(CSRC)/linear_sm100.o $(CSRC)/attention.o $(CSRC)/rowwise.o $(CSRC)/xty.o $(CSRC)/xty_sm100.o $(CSRC)/patch_embed.o $(CSRC)/optim.o $(CSRC)/rankproj.o
+OBJS      := $(CSRC)/api.o $(CSRC)/linear_sm100.o $(CSRC)/attention.o $(CSRC)/attention_sm100.o $(CSRC)/rowwise.o $(CSRC)/xty.o $(CSRC)/xty_sm100.o $(CSRC)/patch_embed.o $(CSRC)/optim.o $(CSRC)/rankproj.o
 LIB       := mtlora_b200/libmtlora_b200.so
 
 all: $(LIB)

@@ -13,6 +13,8 @@
 #include "common.cuh"
 #include "kernels.cuh"
 
+#include <stdlib.h>
+
 namespace mtl {
 
 namespace {
@@ -611,6 +613,11 @@ int launch_win_attn_fwd(const void* qkv, const float* rpb, const float* mask, in
                         float* lse, int B, int H, int W, int C, int nH, int ws, int shift, float scale,
                         float drop_p, uint64_t drop_seed, cudaStream_t stream) {
   if (int e = check_geom(B, H, W, C, nH, ws, shift)) return e;
+  // tcgen05 / TMEM kernel (attention_sm100.cu) unless the caller hands an explicit mask (stand-alone WindowAttention)
+  static const bool legacy = getenv("MTL_ATTN_LEGACY") != nullptr;   // A/B aid
+  if (mask == nullptr && !legacy && win_attn_fwd_umma_supported(C, nH, ws))
+    return launch_win_attn_fwd_umma(qkv, rpb, out, out_drop, lse, B, H, W, C, nH, ws, shift, scale, drop_p, drop_seed,
+                                    stream);
   AttnParams p;
   p.qkv = static_cast<const __nv_bfloat16*>(qkv);
   p.rpb = rpb;

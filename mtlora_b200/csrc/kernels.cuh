@@ -15,6 +15,14 @@ int launch_win_attn_bwd(const void* qkv, const void* dout, const float* rpb, con
                         const float* lse, void* dqkv, float* drpb, int B, int H, int W, int C, int nH, int ws,
                         int shift, float scale, cudaStream_t stream);
 
+// attention_sm100.cu ------------------------------------------------------------------------------
+// tcgen05 / TMEM forward (two windows per 128-row tile, whole-row gathers); same contract as launch_win_attn_fwd without
+// an explicit mask
+bool win_attn_fwd_umma_supported(int C, int nH, int ws);
+int launch_win_attn_fwd_umma(const void* qkv, const float* rpb, void* out, void* out_drop, float* lse, int B, int H,
+                             int W, int C, int nH, int ws, int shift, float scale, float drop_p, uint64_t drop_seed,
+                             cudaStream_t stream);
+
 // rowwise.cu --------------------------------------------------------------------------------------
 // LayerNorm over the last dim of [rows, C] (bf16 in/out, fp32 statistics and affine parameters).
 // merge != 0: input is a (B, H, W, C/4) token grid and each output row is the PatchMerging 2x2 gather

@@ -467,6 +467,12 @@ ATTN_CASES = [
     (2, 7, 7, 24, 7, 0),
     (1, 56, 56, 3, 7, 3),
     (2, 14, 28, 2, 7, 3),
+    # tcgen05 forward (attention_sm100.cu): odd window count (half-empty last 128-row tile), Swin-B head counts (head
+    # pairs), 12 heads, smaller windows
+    (1, 21, 21, 3, 7, 3),
+    (3, 14, 14, 4, 7, 3),
+    (1, 28, 28, 12, 7, 0),
+    (2, 8, 12, 6, 4, 2),
 ]
 
 
