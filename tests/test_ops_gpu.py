@@ -484,8 +484,10 @@ def ref_attention(qkv, rpb, nH, ws, shift, mask):
 
 
 @pytest.mark.parametrize("B,H,W,nH,ws,shift", ATTN_CASES)
-@pytest.mark.parametrize("explicit_mask", [False, True])
-def test_window_attention(ops, B, H, W, nH, ws, shift, explicit_mask):
+@pytest.mark.parametrize("explicit_mask,umma", [(False, False), (True, False), (False, True)])
+def test_window_attention(ops, B, H, W, nH, ws, shift, explicit_mask, umma, monkeypatch):
+    # umma: the opt-in tcgen05 / TMEM forward (attention_sm100.cu, MTL_ATTN_UMMA=1); default: the mma.sync kernel
+    monkeypatch.setenv("MTL_ATTN_UMMA", "1" if umma else "0")
     if explicit_mask and shift == 0:
         pytest.skip("no mask without shift")
     C = 32 * nH
@@ -506,7 +508,9 @@ def test_window_attention(ops, B, H, W, nH, ws, shift, explicit_mask):
     check(drpb, rf.grad, tol=2e-2, what="d relative_position_bias_table")
 
 
-def test_window_attention_dropout_copy(ops):
+@pytest.mark.parametrize("umma", [False, True])
+def test_window_attention_dropout_copy(ops, umma, monkeypatch):
+    monkeypatch.setenv("MTL_ATTN_UMMA", "1" if umma else "0")
     B, H, W, nH, ws = 2, 14, 14, 3, 7
     qkv = bf(dev(detgen.uniform("attd.qkv", (B, H, W, 96 * 3))))
     rpb = dev(detgen.std_uniform("attd.rpb", (169, nH), 0.5))
