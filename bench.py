@@ -582,6 +582,15 @@ def run_ours(a):
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
         return
+    # host-side issue time of one step (queue empty at the start, so the launches never block on the GPU): the step is
+    # GPU-bound as long as this stays below ms_per_step
+    host_ms = []
+    for i in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step(resident[i % 2], i)
+        host_ms.append(1e3 * (time.perf_counter() - t0))
+    torch.cuda.synchronize()
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
@@ -696,6 +705,7 @@ def run_ours(a):
         "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e / a.steps,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
+        "host_issue_ms_per_step": round(statistics.median(host_ms), 3),
         "clocks": clk,
         "roofline": roof,
         "roofline_tensor": roof_tensor,

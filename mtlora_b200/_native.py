@@ -169,6 +169,29 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
+_cur_dev = (None, -1)   # (launch_count at which the device was last queried, its index)
+
+
+def current_device_index():
+    """Index of the current CUDA device, queried from torch at most once per C-ABI call (the argument checks of one
+    op look at ~10 tensors; torch.cuda.current_device() costs about a microsecond each time)."""
+    global _cur_dev
+    if _cur_dev[0] != launch_count:
+        import torch
+        _cur_dev = (launch_count, torch.cuda.current_device())
+    return _cur_dev[1]
+
+
+_raw_stream = None
+
+
 def stream():
+    """cudaStream_t of torch's current stream on the current device (the raw-handle query costs a fraction of a
+    microsecond; torch.cuda.current_stream() builds a Python Stream object every time)."""
+    global _raw_stream
     import torch
+    if _raw_stream is None:
+        _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", False)
+    if _raw_stream:
+        return _raw_stream(current_device_index())
     return torch.cuda.current_stream().cuda_stream

@@ -126,7 +126,8 @@ class LinearEngine:
     def forward(self, x, *, xt=False, gelu=False, gelu_grad=False, residual=None, path_scale=None, rows_per_sample=0,
                 dropout_p=0.0, seed=0, save=True):
         """x [S_in, M, K] bf16 (incl. the appended D(x[0]) stream when dropout_p > 0) -> y, y_act, saved-dict."""
-        w, _, (a_cat, b_cat, _, _) = self.stage()
+        staged = self.stage()
+        w, _, (a_cat, b_cat, _, _) = staged
         bias = self.linear.bias
         bias = None if bias is None else bias.detach().float()
         y, y_act, u = ops.linear_fwd(self.spec, x, w, bias, a_cat, b_cat, x_tasks_given=xt, act_gelu=gelu, gelu_grad=gelu_grad,
@@ -134,8 +135,10 @@ class LinearEngine:
                                      dropout_p=dropout_p, seed=seed, save_u=save)
         saved = None
         if save:
+            # `staged`: the bf16 operand copies this forward ran with — backward uses the same ones (the masters cannot
+            # have changed legitimately in between) instead of re-validating ~10 (data_ptr, _version) keys per layer
             saved = dict(x=x, u=u, xt=xt, dropout_p=dropout_p, seed=seed, path_scale=path_scale,
-                         rows_per_sample=rows_per_sample)
+                         rows_per_sample=rows_per_sample, staged=staged)
         return y, y_act, saved
 
     def backward(self, saved, dy, *, gelu_aux=None, aux_is_grad=False, need_dx=True):
@@ -144,7 +147,7 @@ class LinearEngine:
         DropPath (`path_scale` given in forward): a single-stream layer scales inside the kernels, a multi-stream
         layer pre-scales dy once (header contract of mtl_linear_bwd_input)."""
         spec = self.spec
-        _, wt, (_, _, a_cat_t, b_cat_t) = self.stage()
+        _, wt, (_, _, a_cat_t, b_cat_t) = saved.get("staged") or self.stage()
         ps, rps = saved["path_scale"], saved["rows_per_sample"]
         dy_in, dy_sum = dy, False
         v2 = spec.mode == ops.N.MTL_MODE_MATRIXV2 and spec.S_out > 1   # shared adapter sees the gradient of every stream

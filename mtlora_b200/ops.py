@@ -52,7 +52,7 @@ def _chk(t, dtype, name):
         return
     if not t.is_cuda:
         raise RuntimeError(f"{name}: expected a CUDA tensor — mtlora_b200 has no CPU path")
-    if t.device.index != torch.cuda.current_device():
+    if t.device.index != N.current_device_index():
         raise RuntimeError(f"{name}: tensor lives on {t.device} but the current CUDA device is "
                            f"cuda:{torch.cuda.current_device()} (one process per GPU; wrap the call in torch.cuda.device)")
     if t.dtype != dtype:

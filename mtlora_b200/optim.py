@@ -78,7 +78,13 @@ class FlatAdamW(torch.optim.Optimizer):
         for i, p in enumerate(ps):
             s = self._segs_host[i]
             s.param, s.grad, s.offset, s.numel, s.group = p.data_ptr(), None, offs[i], p.numel(), groups[i]
-        self._segs_dev = torch.zeros(ctypes.sizeof(self._segs_host), dtype=torch.uint8, device=dev)
+        nbytes = ctypes.sizeof(self._segs_host)
+        self._segs_dev = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        # the table travels through a small ring of pinned staging buffers with non-blocking copies: a blocking copy from
+        # pageable memory would synchronise the stream (the whole step) every time a gradient pointer changes
+        self._pin = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(4)]
+        self._pin_ev = [None] * 4
+        self._pin_k = 0
         self._grad_key = None
         assert N.load().mtl_opt_seg_size() == ctypes.sizeof(N.OptSeg)
         # torch.optim.AdamW-shaped per-parameter state (views into the flat buffers) for state_dict() / checkpoints
@@ -125,8 +131,15 @@ class FlatAdamW(torch.optim.Optimizer):
                     raise TypeError("FlatAdamW: gradients must be contiguous fp32 tensors on the parameter's device")
                 self._segs_host[i].grad = None if g is None else g.data_ptr()
                 self._segs_host[i].param = p.data_ptr()
-            host = torch.frombuffer(bytearray(bytes(self._segs_host)), dtype=torch.uint8)
-            self._segs_dev.copy_(host)
+            k = self._pin_k
+            self._pin_k = (k + 1) % len(self._pin)
+            if self._pin_ev[k] is not None:
+                self._pin_ev[k].synchronize()      # its previous upload (4 table changes ago) has long completed
+            ctypes.memmove(self._pin[k].data_ptr(), ctypes.addressof(self._segs_host), ctypes.sizeof(self._segs_host))
+            self._segs_dev.copy_(self._pin[k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._pin_ev[k] = ev
             self._grad_key = key
         if not any(key):
             return loss
