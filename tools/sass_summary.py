@@ -20,7 +20,8 @@ def main():
         m = re.search(r"Function : (\S+)", line)
         if m:
             kern = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
-            kern = re.sub(r"\(.*", "", kern).replace("mtl::(anonymous namespace)::", "").replace("void ", "")
+            kern = kern.replace("mtl::(anonymous namespace)::", "").replace("void ", "")
+            kern = re.sub(r"\((?!anonymous).*", "", kern)
             counts[kern] = collections.Counter()
             continue
         m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
