@@ -662,9 +662,8 @@ int launch_win_attn_bwd(const void* qkv, const void* dout, const float* rpb, con
   int gx = n_win;
   const int cap = (148 * 3 + nH - 1) / nH;  // 3 resident CTAs per SM (register-limited), strided over windows
   if (gx > cap) gx = cap;
-  static cudaError_t attr_err = cudaFuncSetAttribute(win_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    kBwdSmemBytes);
-  MTL_CHECK_CUDA(attr_err);
+  static bool attr_done[64] = {};
+  MTL_CHECK_CUDA(ensure_max_dyn_smem(attr_done, win_attn_bwd_kernel, kBwdSmemBytes));
   win_attn_bwd_kernel<<<dim3(gx, nH), 128, kBwdSmemBytes, stream>>>(p); note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
   return 0;

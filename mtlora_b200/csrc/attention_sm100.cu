@@ -393,10 +393,7 @@ int launch_win_attn_fwd_umma(const void* qkv, const float* rpb, void* out, void*
   MTL_CHECK_CUDA(cudaGetDevice(&dev));
   MTL_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   static bool attr_done[64] = {};
-  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-    MTL_CHECK_CUDA(cudaFuncSetAttribute(win_attn_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done[dev] = true;
-  }
+  MTL_CHECK_CUDA(ensure_max_dyn_smem(attr_done, win_attn_fwd_umma_kernel, 227 * 1024));
   const int grid = p.n_units < n_sm ? p.n_units : n_sm;
   win_attn_fwd_umma_kernel<<<grid, kThreads, smem, stream>>>(p);
   note_launch();

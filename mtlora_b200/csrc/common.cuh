@@ -34,6 +34,21 @@ void note_launch();
     }                                                                                  \
   } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE property: set it once per (kernel call site, device)
+// so that a process driving several GPUs launches correctly on all of them. `done` is the call site's static table.
+// (Benign race: two threads may both set the attribute the first time.)
+template <typename F>
+inline cudaError_t ensure_max_dyn_smem(bool (&done)[64], F kernel, int bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64 || !done[dev]) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+  }
+  return e;
+}
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------
 // Small device utilities

@@ -1166,23 +1166,21 @@ int launch_linear(LinPlan p, const void* x, const void* wm, const void* down, co
       {mtl_linear_kernel<LIN_EP_MUL_AUX, false, false>, mtl_linear_kernel<LIN_EP_MUL_AUX, false, true>},
       {mtl_linear_kernel<LIN_EP_NONE, true, false>, mtl_linear_kernel<LIN_EP_NONE, true, true>}};
   static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
   static int max_ctas = -1;
   static uint32_t wait_hint = 1000u;
   std::call_once(attr_once, []() {
-    for (int a = 0; a < 6; ++a)
-      for (int c = 0; c < 2; ++c) {
-        cudaError_t e = cudaFuncSetAttribute(kernels[a][c], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) attr_err = e;
-      }
     const char* e = getenv("MTL_LINEAR_MAX_CTAS");  // debugging aid: 0 = one CTA per work item (non-persistent)
     max_ctas = e ? atoi(e) : -1;
     const char* h = getenv("MTL_WAIT_HINT_NS");      // mbarrier.try_wait suspend-time hint (tuning aid)
     if (h) wait_hint = static_cast<uint32_t>(atoi(h));
   });
-  MTL_CHECK_CUDA(attr_err);
   p.wait_hint_ns = wait_hint;
   static const char* trace_path = getenv("MTL_LINEAR_TRACE");
+  static bool attr_done[12][64] = {};   // per kernel variant and device
+  {
+    const int ki = (p.res != nullptr ? 5 : p.ep_mode) * 2 + (trace_path != nullptr ? 1 : 0);
+    MTL_CHECK_CUDA(ensure_max_dyn_smem(attr_done[ki], kernels[ki / 2][ki % 2], 227 * 1024));
+  }
   p.trace = nullptr;
   if (trace_path != nullptr) {
     MTL_CHECK_CUDA(cudaMalloc(&p.trace, 4 * 2048 * sizeof(unsigned long long)));

@@ -99,12 +99,7 @@ template <int R>
 int launch_r(const void* x, const void* down, void* out, int M, int K, float scale, cudaStream_t stream) {
   constexpr int smem = kStages * (kRows + R) * 128 + 128;
   static bool attr_done[64] = {};
-  int dev = 0;
-  MTL_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_done[dev]) {   // the attribute is per device (benign race: setting it twice is fine)
-    MTL_CHECK_CUDA(cudaFuncSetAttribute(rank_project_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done[dev] = true;
-  }
+  MTL_CHECK_CUDA(ensure_max_dyn_smem(attr_done, rank_project_kernel<R>, smem));
   rank_project_kernel<R><<<(M + kRows - 1) / kRows, kThreads, smem, stream>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(down), static_cast<__nv_bfloat16*>(out), M,
       K, scale);

@@ -389,13 +389,8 @@ int launch_xty_groups(const XtyOperand* wide, const XtyOperand* rank, const XtyJ
       return e;
   }
   const uint32_t smem_bytes = XG_STAGES * XG_STAGE_BYTES + 1024 + 1024;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, []() {
-    attr_err = cudaFuncSetAttribute(xty_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    XG_STAGES * XG_STAGE_BYTES + 2048);
-  });
-  MTL_CHECK_CUDA(attr_err);
+  static bool attr_done[64] = {};
+  MTL_CHECK_CUDA(ensure_max_dyn_smem(attr_done, xty_umma_kernel, XG_STAGES * XG_STAGE_BYTES + 2048));
   const int grid = p.n_units < n_sm ? p.n_units : n_sm;
   xty_umma_kernel<<<grid, XG_THREADS, smem_bytes, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
   note_launch();
