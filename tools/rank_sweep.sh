@@ -12,7 +12,7 @@ for r in 4 8 16 32 64 128; do
   for rt in 4 $r; do
     [ "$rt" = "$r" ] && [ "$r" = 4 ] && continue      # same point as rt = 4
     [ "$rt" = 128 ] && continue                        # 5 x 128 = 640 columns: beyond the kernel's 320
-    timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --r-shared "$r" --r-task "$rt" 2>/dev/null \
+    timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras --r-shared "$r" --r-task "$rt" 2>/dev/null \
       | tail -1 >> "$out" || echo "{\"r_shared\": $r, \"r_task\": $rt, \"failed\": true}" >> "$out"
   done
 done
