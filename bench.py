@@ -552,6 +552,7 @@ def run_ours(a):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         last = None
+        stamps = [time.perf_counter()]
         if e2e:
             prefetch(0)
         for i in range(n_steps):
@@ -562,6 +563,7 @@ def run_ours(a):
                 if i + 1 < n_steps:
                     prefetch(i + 1)                # H2D of the next batch overlaps this step's kernels
                 last = loss.item()                 # D2H read of the step's result
+                stamps.append(time.perf_counter())
             else:
                 last = step(resident[i % 2], i)
         e1.record()
@@ -570,7 +572,9 @@ def run_ours(a):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item(), _native.kernel_launches() - k0, float(last)
+        per_step = [1e3 * (b - a_) for a_, b in zip(stamps, stamps[1:])]
+        timed.per_step = per_step
+        return t.item(), _native.kernel_launches() - k0, float(last.detach() if hasattr(last, "detach") else last)
 
     # warm-up (also stages the bf16 copies of the frozen weights)
     for i in range(a.warmup):
@@ -597,6 +601,7 @@ def run_ours(a):
     ms_dev, launches, loss_dev = timed(a.steps, e2e=False)
     timed(min(a.warmup, 3), e2e=True)              # warm the end-to-end loop (copy stream, staging buffers)
     ms_e2e, _, loss_e2e = timed(a.steps, e2e=True)
+    e2e_steps = sorted(getattr(timed, "per_step", []) or [0.0])
     clk = clocks.stop() if rank == 0 else None
 
     # per-call CUDA-event profile of 2 more steps: time share per C-ABI entry point + roofline of the fused linear
@@ -705,7 +710,10 @@ def run_ours(a):
                    "alternating input batches", "loss_dev": loss_dev, "loss_e2e": loss_e2e,
                    "optimizer": "torch fused AdamW" if a.torch_optimizer else "mtlora_b200 FlatAdamW (one launch)"},
         "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e / a.steps,
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                # host-clock spread of the individual steps (rank 0): a slow host or a contended PCIe link shows here
+                "step_ms_min_median_max": [round(e2e_steps[0], 2), round(e2e_steps[len(e2e_steps) // 2], 2),
+                                           round(e2e_steps[-1], 2)]},
         "gpu_launches": launches,
         "host_issue_ms_per_step": round(statistics.median(host_ms), 3),
         "clocks": clk,
