@@ -576,6 +576,11 @@ def run_ours(a):
         timed.per_step = per_step
         return t.item(), _native.kernel_launches() - k0, float(last.detach() if hasattr(last, "detach") else last)
 
+    # the clocks sampler (nvidia-smi -lms) is started BEFORE the warm-up: its start-up (NVML initialisation, ~1-2 s of
+    # driver queries) must not fall into the timed region it is there to observe
+    clocks = Clocks(local)
+    if rank == 0 and not a.ncu_range:
+        clocks.start()
     # warm-up (also stages the bf16 copies of the frozen weights)
     for i in range(a.warmup):
         step(resident[i % 2], i)
@@ -595,9 +600,6 @@ def run_ours(a):
         step(resident[i % 2], i)
         host_ms.append(1e3 * (time.perf_counter() - t0))
     torch.cuda.synchronize()
-    clocks = Clocks(local)
-    if rank == 0:
-        clocks.start()
     ms_dev, launches, loss_dev = timed(a.steps, e2e=False)
     timed(min(a.warmup, 3), e2e=True)              # warm the end-to-end loop (copy stream, staging buffers)
     ms_e2e, _, loss_e2e = timed(a.steps, e2e=True)
