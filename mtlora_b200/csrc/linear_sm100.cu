@@ -910,11 +910,55 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 }  // namespace
 
+namespace {
+// Descriptor cache: a training step re-launches the same ~100 layer shapes on buffers the caching
+// allocator hands back at the same addresses, so the 128-byte tensor maps are looked up by (base, dims, box, swizzle,
+// pitch) instead of being re-encoded by the driver nine times per launch. Small direct-mapped table behind a mutex; a
+// descriptor only describes addresses and strides, so a stale entry is impossible — equal keys give equal maps.
+struct TmapKey {
+  const void* base;
+  uint64_t d0, d1, d2, pitch;
+  uint32_t b0, b1, swz;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && pitch == o.pitch && b0 == o.b0 && b1 == o.b1 &&
+           swz == o.swz;
+  }
+};
+struct TmapSlot {
+  TmapKey key;
+  CUtensorMap map;
+  bool valid;
+};
+constexpr int kTmapSlots = 4096;
+TmapSlot* tmap_table() {
+  static TmapSlot* t = new TmapSlot[kTmapSlots]();
+  return t;
+}
+std::mutex g_tmap_mu;
+inline size_t tmap_hash(const TmapKey& k) {
+  uint64_t h = reinterpret_cast<uintptr_t>(k.base) * 0x9E3779B97F4A7C15ull;
+  h ^= (k.d0 * 0xBF58476D1CE4E5B9ull) ^ (k.d1 * 0x94D049BB133111EBull) ^ (k.d2 << 7) ^ (k.pitch << 29) ^
+       (static_cast<uint64_t>(k.b0) << 40) ^ (static_cast<uint64_t>(k.b1) << 52) ^ (static_cast<uint64_t>(k.swz) << 60);
+  h ^= h >> 31;
+  return static_cast<size_t>(h) % kTmapSlots;
+}
+}  // namespace
+
 // bf16 row-major [d2][d1][d0] tensor (d0 contiguous), box = (b0, b1, 1), 128-byte swizzle unless stated.
 // pitch = elements between consecutive rows (0: d0, i.e. densely packed).
 int make_tmap(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,
               uint32_t b1, CUtensorMapSwizzle swz, uint64_t pitch) {
   if (pitch == 0) pitch = d0;
+  const TmapKey key{base, d0, d1, d2, pitch, b0, b1, static_cast<uint32_t>(swz)};
+  const size_t slot = tmap_hash(key);
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    const TmapSlot& s = tmap_table()[slot];
+    if (s.valid && s.key == key) {
+      *tm = s.map;
+      return 0;
+    }
+  }
   auto fn = get_encode_fn();
   MTL_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   MTL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer not 16-byte aligned");
@@ -930,11 +974,35 @@ int make_tmap(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint6
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MTL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (dims %llu,%llu,%llu box %u,%u)",
               (int)r, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, b0, b1);
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    TmapSlot& s = tmap_table()[slot];
+    s.key = key;
+    s.map = *tm;
+    s.valid = true;
+  }
   return 0;
 }
 
 namespace {
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// Tuning / debugging switches of the planner, read from the environment once per process.
+struct PlanEnv {
+  bool no_dshared;
+  int force_bn, force_splits;
+  PlanEnv() {
+    no_dshared = getenv("MTL_LINEAR_NO_DSHARED") != nullptr;
+    const char* e = getenv("MTL_LINEAR_BN");
+    force_bn = e ? atoi(e) : 0;
+    e = getenv("MTL_LINEAR_SPLITS");
+    force_splits = e ? atoi(e) : 0;
+  }
+};
+const PlanEnv& plan_env() {
+  static const PlanEnv env;
+  return env;
+}
 }  // namespace
 
 int plan_linear(LinPlan& p, int n_sm, uint32_t* smem_bytes_out) {
@@ -1004,15 +1072,15 @@ int plan_linear(LinPlan& p, int n_sm, uint32_t* smem_bytes_out) {
     // (measured at K = 96 too: 128-column items beat 64-column ones by 14-23 % — the per-item cost of the epilogue
     // protocol outweighs the lost overlap of the two groups on the tiny delta products)
     if (p.S_out == 1 && p.Nn > 64 && u_cols + 3 * 128 <= 512 && fits_smem(128, want_slabs) &&
-        getenv("MTL_LINEAR_NO_DSHARED") == nullptr) {
+        !plan_env().no_dshared) {
       bn = 128;
       p.n_pbuf = 2;
       p.n_dbuf = 1;
       p.d_shared = 1;
     }
   }
-  if (const char* e = getenv("MTL_LINEAR_BN")) {   // tuning aid: force the chunk width (merged mode only)
-    const int fb = atoi(e);
+  if (plan_env().force_bn > 0) {   // tuning aid (MTL_LINEAR_BN): force the chunk width (merged mode only)
+    const int fb = plan_env().force_bn;
     if (!multi && (fb == 64 || fb == 128 || fb == 192) && cols(fb, 0, 1) <= 512) {
       bn = fb;
       p.n_dbuf = cols(fb, 0, 2) <= 512 ? 2 : 1;
@@ -1080,8 +1148,8 @@ int plan_linear(LinPlan& p, int n_sm, uint32_t* smem_bytes_out) {
       }
     }
   }
-  if (const char* e = getenv("MTL_LINEAR_SPLITS")) {
-    const int fs = atoi(e);
+  if (plan_env().force_splits > 0) {   // tuning aid (MTL_LINEAR_SPLITS)
+    const int fs = plan_env().force_splits;
     if (fs >= 1 && fs <= p.n_chunks) p.n_splits = fs;
   }
   p.n_work = m_tiles * p.n_splits;

@@ -15,7 +15,6 @@
 namespace mtl {
 namespace {
 
-constexpr int kRows = 64;      // rows per CTA
 constexpr int kBK = 64;        // contraction elements per stage (one 128-byte smem row)
 constexpr int kStages = 3;
 constexpr int kThreads = 128;
@@ -23,11 +22,14 @@ constexpr int kThreads = 128;
 // byte offset of 16-byte chunk `c` of row `r` in a [rows][64] bf16 tile with an XOR swizzle (conflict-free ldmatrix)
 __device__ __forceinline__ uint32_t tile_off(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
 
-template <int R>
-__global__ void __launch_bounds__(kThreads, 3)
+// ROWS = 64: warp w owns rows 16w..16w+15 and all R columns. ROWS = 32 (few row tiles: M = 25088 gives only 392 CTAs of
+// 64 rows for 148 SMs): warp w owns rows 16(w & 1).. and the column half (w >> 1), twice as many CTAs in flight.
+template <int R, int kRows>
+__global__ void __launch_bounds__(kThreads, kRows == 64 ? 3 : 5)
 rank_project_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ down,
                     __nv_bfloat16* __restrict__ out, int M, int K, float scale) {
   constexpr int kStageBytes = (kRows + R) * 128;
+  constexpr int CW = kRows == 64 ? R : R / 2;        // columns per warp
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = (smem_u32(smem) + 127u) & ~127u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -53,9 +55,11 @@ rank_project_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
     }
   };
 
-  float acc[R / 8][4];
+  const int wrow = kRows == 64 ? warp * 16 : (warp & 1) * 16;
+  const int wcol = kRows == 64 ? 0 : (warp >> 1) * CW;
+  float acc[CW / 8][4];
 #pragma unroll
-  for (int j = 0; j < R / 8; ++j)
+  for (int j = 0; j < CW / 8; ++j)
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
 
@@ -72,11 +76,11 @@ rank_project_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
 #pragma unroll
     for (int kk = 0; kk < kBK / 16; ++kk) {
       uint32_t a[4];
-      ldmatrix_x4(a, xs + tile_off(warp * 16 + (lane & 15), kk * 2 + (lane >> 4)));
+      ldmatrix_x4(a, xs + tile_off(wrow + (lane & 15), kk * 2 + (lane >> 4)));
 #pragma unroll
-      for (int jp = 0; jp < R / 16; ++jp) {
+      for (int jp = 0; jp < CW / 16; ++jp) {
         uint32_t b[4];
-        ldmatrix_x4(b, ds + tile_off(jp * 16 + (lane & 7) + ((lane >> 4) << 3), kk * 2 + ((lane >> 3) & 1)));
+        ldmatrix_x4(b, ds + tile_off(wcol + jp * 16 + (lane & 7) + ((lane >> 4) << 3), kk * 2 + ((lane >> 3) & 1)));
         const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]};
         mma_bf16_16816(acc[2 * jp], a, b0);
         mma_bf16_16816(acc[2 * jp + 1], a, b1);
@@ -86,26 +90,33 @@ rank_project_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
   cp_async_wait<0>();
   // epilogue: scale, round, store (row g and g + 8 of the warp's 16 rows; columns 2t, 2t + 1 of every 8-column tile)
   const int g = lane >> 2, t = lane & 3;
-  const int r0 = m0 + warp * 16 + g, r1 = r0 + 8;
+  const int r0 = m0 + wrow + g, r1 = r0 + 8;
 #pragma unroll
-  for (int j = 0; j < R / 8; ++j) {
-    const int col = j * 8 + 2 * t;
+  for (int j = 0; j < CW / 8; ++j) {
+    const int col = wcol + j * 8 + 2 * t;
     if (r0 < M) *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(r0) * R + col) = pack_bf16x2(acc[j][0] * scale, acc[j][1] * scale);
     if (r1 < M) *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(r1) * R + col) = pack_bf16x2(acc[j][2] * scale, acc[j][3] * scale);
   }
 }
 
-template <int R>
-int launch_r(const void* x, const void* down, void* out, int M, int K, float scale, cudaStream_t stream) {
+template <int R, int kRows>
+int launch_rr(const void* x, const void* down, void* out, int M, int K, float scale, cudaStream_t stream) {
   constexpr int smem = kStages * (kRows + R) * 128 + 128;
   static bool attr_done[64] = {};
-  MTL_CHECK_CUDA(ensure_max_dyn_smem(attr_done, rank_project_kernel<R>, smem));
-  rank_project_kernel<R><<<(M + kRows - 1) / kRows, kThreads, smem, stream>>>(
+  MTL_CHECK_CUDA(ensure_max_dyn_smem(attr_done, rank_project_kernel<R, kRows>, smem));
+  rank_project_kernel<R, kRows><<<(M + kRows - 1) / kRows, kThreads, smem, stream>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(down), static_cast<__nv_bfloat16*>(out), M,
       K, scale);
   note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int R>
+int launch_r(const void* x, const void* down, void* out, int M, int K, float scale, cudaStream_t stream) {
+  // (a 32-row variant — twice the CTAs, each warp half the columns — measured 5-7 % slower at M = 25088: the Down tile is
+  // then re-read by twice as many CTAs and every warp issues fewer MMAs per ldmatrix)
+  return launch_rr<R, 64>(x, down, out, M, K, scale, stream);
 }
 
 }  // namespace
