@@ -5,7 +5,9 @@
  * (kernels/window_process/swin_window_process.cpp:127-132). Each entry point below names the reference
  * interface it replaces (paths relative to the reference checkout). All pointers are DEVICE pointers owned by
  * the caller (torch caching allocator in the Python host layer), every call is asynchronous on `stream`, nothing
- * is allocated or freed inside, and the library keeps no mutable global state besides a thread-local error string.
+ * is allocated or freed on the device inside. Process-wide state, all of it behind a mutex or atomic: a thread-local
+ * error string, a launch counter, per-device "shared-memory attribute set" flags and a cache of TMA descriptors keyed
+ * by (base pointer, dims, box, swizzle) — a descriptor only encodes addresses and strides, so it cannot go stale.
  *
  * Conventions
  *   - activations are bf16, row-major, "stream-stacked": [S, M, C] where stream 0 is the task-shared stream and

@@ -636,7 +636,7 @@ int launch_win_attn_fwd(const void* qkv, const float* rpb, const float* mask, in
   p.g = WinGeom{H, W, ws, shift, H / ws, W / ws, ws * ws};
   const int n_win = B * p.g.nwh * p.g.nww;
   int gx = n_win;
-  const int cap = (148 * 8 + nH - 1) / nH;  // ~8 CTAs per SM in flight across heads
+  const int cap = (sm_count() * 8 + nH - 1) / nH;  // ~8 CTAs per SM in flight across heads
   if (gx > cap) gx = cap;
   win_attn_fwd_kernel<<<dim3(gx, nH), 128, 0, stream>>>(p); note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
@@ -660,7 +660,7 @@ int launch_win_attn_bwd(const void* qkv, const void* dout, const float* rpb, con
   p.g = WinGeom{H, W, ws, shift, H / ws, W / ws, ws * ws};
   const int n_win = B * p.g.nwh * p.g.nww;
   int gx = n_win;
-  const int cap = (148 * 3 + nH - 1) / nH;  // 3 resident CTAs per SM (register-limited), strided over windows
+  const int cap = (sm_count() * 3 + nH - 1) / nH;  // 3 resident CTAs per SM (register-limited), strided over windows
   if (gx > cap) gx = cap;
   static bool attr_done[64] = {};
   MTL_CHECK_CUDA(ensure_max_dyn_smem(attr_done, win_attn_bwd_kernel, kBwdSmemBytes));

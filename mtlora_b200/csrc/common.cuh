@@ -49,6 +49,19 @@ inline cudaError_t ensure_max_dyn_smem(bool (&done)[64], F kernel, int bytes) {
   return e;
 }
 
+// Multiprocessor count of the current device (148 on a B200), queried once per device; grid caps are multiples of it.
+inline int sm_count() {
+  static int cached[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------
 // Small device utilities

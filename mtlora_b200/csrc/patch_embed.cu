@@ -142,7 +142,7 @@ int launch_patch_embed_fwd(const float* x, const float* w, const float* bias, co
                      static_cast<__nv_bfloat16*>(patches), mean, rstd, B, H, W, E, eps};
   const long n_pair = (static_cast<long>(B) * (H / 4) * (W / 4) + 1) / 2;
   long blocks = (n_pair + PE_WARPS - 1) / PE_WARPS;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   const size_t sm = (static_cast<size_t>(PE_K) * E + PE_WARPS * 2 * PE_K) * sizeof(float);
   if (E == 96) patch_embed_fwd_kernel<3><<<static_cast<unsigned>(blocks), 32 * PE_WARPS, sm, stream>>>(p);
   else patch_embed_fwd_kernel<4><<<static_cast<unsigned>(blocks), 32 * PE_WARPS, sm, stream>>>(p);

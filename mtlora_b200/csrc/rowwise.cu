@@ -710,7 +710,7 @@ __global__ void cast_transpose_kernel(const float* __restrict__ w, __nv_bfloat16
 
 int grid_for(long work, int block) {
   long g = (work + block - 1) / block;
-  const long cap = 148L * 16;
+  const long cap = sm_count() * 16L;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return static_cast<int>(g);
@@ -730,7 +730,7 @@ int launch_layernorm_fwd(const void* x, const float* gamma, const float* beta, v
   if (ln_fast_shape(C, &lpr, &vpt)) {
     const long row_groups = (rows + (32 / lpr) - 1) / (32 / lpr);
     long grid = (row_groups + 7) / 8;
-    if (grid > 148L * 16) grid = 148L * 16;
+    if (grid > sm_count() * 16L) grid = sm_count() * 16L;
     const unsigned g = static_cast<unsigned>(grid);
     MTL_LN_CASES(ln_fwd_launch, p, g, stream)
   } else {
@@ -755,14 +755,14 @@ int launch_layernorm_bwd(const void* dy, const void* x, const float* gamma, cons
   if (ln_fast_shape(C, &lpr, &vpt)) {
     const long row_groups = (rows + (32 / lpr) - 1) / (32 / lpr);
     long grid = (row_groups + 7) / 8;
-    if (grid > 148L * 4) grid = 148L * 4;
+    if (grid > sm_count() * 4L) grid = sm_count() * 4L;
     const unsigned g = static_cast<unsigned>(grid);
     MTL_LN_CASES(ln_bwd_launch, p, g, stream)
     note_launch();
     MTL_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
-  long ctas = 148L * 4;
+  long ctas = sm_count() * 4L;
   long rpc = (rows + ctas - 1) / ctas;
   if (rpc < 8) rpc = 8;
   p.rows_per_cta = static_cast<int>(rpc);

@@ -131,7 +131,7 @@ int launch_xty(const void* P, long ldp, const void* Q, long ldq, float* C, long 
   p.q_gelu = q_gelu;
   p.alpha = alpha;
   const int at = (a + TA - 1) / TA, bt = (b + TB - 1) / TB;
-  long splits = (148L * 4 + at * bt - 1) / (at * bt);
+  long splits = (sm_count() * 4L + at * bt - 1) / (at * bt);
   const long max_splits = (M + 4 * TM - 1) / (4 * TM);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
