@@ -614,7 +614,7 @@ int launch_win_attn_fwd(const void* qkv, const float* rpb, const float* mask, in
                         float drop_p, uint64_t drop_seed, cudaStream_t stream) {
   if (int e = check_geom(B, H, W, C, nH, ws, shift)) return e;
   // MTL_ATTN_UMMA=1 selects the tcgen05 / TMEM forward (attention_sm100.cu). It is parity-green but measured SLOWER than
-  // the mma.sync kernel below on every Swin stage (B200, batch 32: 0.39 vs 0.15 ms at stage 0, profiles/r02_ncu_attn_umma.json):
+  // the mma.sync kernel below on every Swin stage (B200, batch 32: 0.34 vs 0.15 ms at stage 0, profiles/r02_ncu_attn_umma.json):
   // a 49-token window with head_dim 32 is 0.3 MFLOP of tensor work per (window, head), so the kernel is bound by the
   // CUDA-core softmax / bias work and by the TMEM -> registers -> smem round trip of P, which the register-resident
   // mma.sync formulation does not have. The product path therefore stays on the kernel below.

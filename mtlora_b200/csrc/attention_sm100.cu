@@ -34,7 +34,8 @@ constexpr int kThreads = 32 * (kSoftmaxWarps + 1 + kProducerWarps);
 constexpr int kProducers = 32 * kProducerWarps;
 constexpr int kSoftmax = 32 * kSoftmaxWarps;
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr uint32_t kWaitHintNs = 200u;   // mbarrier.try_wait suspend-time hint: the chains here are sub-microsecond
+constexpr uint32_t kWaitHintNs = 2000u;  // mbarrier.try_wait suspend-time hint (the hardware wakes the thread on completion;
+                                         // a short hint only multiplies the polling instructions: 200 ns cost ~20 M of 118 M)
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -90,8 +91,8 @@ __global__ void __launch_bounds__(kThreads, 1) win_attn_fwd_umma_kernel(const UA
   int* reg_s = reinterpret_cast<int*>(gen + kTileBytes);            // [2][128] region ids of the unit's tokens (seam)
   float* xm_s = reinterpret_cast<float*>(reg_s + 256);              // [2][128] row maxima of the two column halves
   float* xl_s = xm_s + 256;                                         // [2][128] row sums
-  float* bias_s = xl_s + 256;                                       // [nH][tbl], pre-multiplied by log2 e
-  const uint32_t bar0 = (base + kTileBytes + (768 + p.nH * tbl) * 4 + 15u) & ~15u;
+  float* bias_s = xl_s + 256;                // [nH][tbl + 1], pre-multiplied by log2 e; entry tbl = -inf (padded keys)
+  const uint32_t bar0 = (base + kTileBytes + (768 + p.nH * (tbl + 1)) * 4 + 15u) & ~15u;
   auto qkv_full = [&](int b) { return bar0 + 8u * b; };
   auto qkv_empty = [&](int b) { return bar0 + 8u * (2 + b); };
   auto s_full = [&](int b) { return bar0 + 8u * (4 + b); };
@@ -109,9 +110,9 @@ __global__ void __launch_bounds__(kThreads, 1) win_attn_fwd_umma_kernel(const UA
   // ---- one-time setup: zero the operand tiles (padding rows / off-diagonal P blocks stay zero), tables, barriers ----
   for (uint32_t i = threadIdx.x; i < static_cast<uint32_t>(kTileBytes) / 16; i += kThreads)
     reinterpret_cast<uint4*>(gen)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = threadIdx.x; i < p.nH * tbl; i += kThreads) {
-    const int h = i / tbl, e = i - h * tbl;
-    bias_s[i] = p.rpb[e * p.nH + h] * kLog2e;
+  for (int i = threadIdx.x; i < p.nH * (tbl + 1); i += kThreads) {
+    const int h = i / (tbl + 1), e = i - h * (tbl + 1);
+    bias_s[i] = e < tbl ? p.rpb[e * p.nH + h] * kLog2e : -INFINITY;
   }
   if (threadIdx.x == 0) {
     for (int b = 0; b < 2; ++b) {
@@ -227,15 +228,18 @@ __global__ void __launch_bounds__(kThreads, 1) win_attn_fwd_umma_kernel(const UA
     const float scale2 = p.scale * kLog2e;
     const uint32_t thr = dropout_threshold(p.drop_p);
     const float keep_scale = 1.f / (1.f - p.drop_p);
-    // bias-table offsets of this thread's 32 key columns (the same for every unit and head) and their validity
-    int koff[32];
-    uint32_t kvalid = 0;
+    // bias-table entry of (this query, key column c) for this thread's 32 key columns — the same for every unit and head
+    // (a head only shifts the table base); padded key columns point at the table's -inf sentinel
+    int bidx[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
       const int j = half * 32 + c, jy = j / p.ws, jx = j - jy * p.ws;
-      koff[c] = j < p.N ? jy * (2 * p.ws - 1) + jx : 0;
-      if (j < p.N) kvalid |= 1u << c;
+      bidx[c] = j < p.N ? (tok_ok ? bq - (jy * (2 * p.ws - 1) + jx) : 0) : tbl;
     }
+    // this row's four 16-byte chunk slots of the swizzled P tile (fixed per thread)
+    uint32_t poff[4];
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) poff[c8] = wsel * kAtomBytes + sw128_offset(row, half * 32 + c8 * 8);
     const int pair_bar = 2 + quad;                 // named barrier of the two warps sharing this quadrant's rows
     uint32_t it = 0, sc = 0, pc = 0, oc[2] = {0, 0};
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it) {
@@ -306,17 +310,18 @@ __global__ void __launch_bounds__(kThreads, 1) win_attn_fwd_umma_kernel(const UA
         tc_fence_before();
         mbar_arrive(s_empty(sb));
         ++sc;
-        const float* bias_h = bias_s + (head0 + j) * tbl + bq;
+        const float* bias_h = bias_s + (head0 + j) * (tbl + 1);
         float s[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) s[c] = fmaf(__uint_as_float(sr[c >> 4][c & 15]), scale2, bias_h[bidx[c]]);
+        if (diff != 0) {   // seam windows only: keys of another region get the reference's -100 (:318-319)
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if ((diff >> c) & 1u) s[c] += -100.0f * kLog2e;
+        }
         float mx = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          float v = fmaf(__uint_as_float(sr[c >> 4][c & 15]), scale2, bias_h[-koff[c]]);
-          if ((diff >> c) & 1u) v += -100.0f * kLog2e;
-          v = ((kvalid >> c) & 1u) ? v : -INFINITY;
-          s[c] = v;
-          mx = fmaxf(mx, v);
-        }
+        for (int c = 0; c < 32; ++c) mx = fmaxf(mx, s[c]);
         xm_s[half * 128 + row] = mx;
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
         mx = fmaxf(mx, xm_s[(half ^ 1) * 128 + row]);
@@ -335,13 +340,13 @@ __global__ void __launch_bounds__(kThreads, 1) win_attn_fwd_umma_kernel(const UA
         // P row -> K-major swizzled tile: keys of window `wsel` live in atom `wsel`
         const uint32_t pb = pc & 1u;
         mbar_wait(p_empty(pb), ((pc >> 1) & 1u) ^ 1u, kWaitHintNs);
-        uint8_t* pa = p_gen + pb * 2 * kAtomBytes + wsel * kAtomBytes;
+        uint8_t* pa = p_gen + pb * 2 * kAtomBytes;
 #pragma unroll
         for (int c8 = 0; c8 < 4; ++c8) {
           uint32_t w[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) w[e] = pack_bf16x2(s[c8 * 8 + 2 * e] * inv, s[c8 * 8 + 2 * e + 1] * inv);
-          *reinterpret_cast<uint4*>(pa + sw128_offset(row, half * 32 + c8 * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(pa + poff[c8]) = make_uint4(w[0], w[1], w[2], w[3]);
         }
         fence_proxy_async_smem();
         mbar_arrive(p_full(pb));
@@ -387,7 +392,7 @@ int launch_win_attn_fwd_umma(const void* qkv, const float* rpb, void* out, void*
   p.n_hg = (nH + 1) / 2;
   p.n_units = ((p.n_win + 1) / 2) * p.n_hg;
   const int tbl = (2 * ws - 1) * (2 * ws - 1);
-  const size_t smem = 1024 + 10 * static_cast<size_t>(kAtomBytes) + (768 + static_cast<size_t>(nH) * tbl) * 4 + 16 + 32 * 8;
+  const size_t smem = 1024 + 10 * static_cast<size_t>(kAtomBytes) + (768 + static_cast<size_t>(nH) * (tbl + 1)) * 4 + 16 + 32 * 8;
   MTL_REQUIRE(smem <= 227 * 1024, "attention (tcgen05): shared memory %zu exceeds 227 KiB", smem);
   int dev = 0, n_sm = 148;
   MTL_CHECK_CUDA(cudaGetDevice(&dev));
