@@ -58,6 +58,8 @@ class FlatAdamW(torch.optim.Optimizer):
         if not ps:
             raise ValueError("FlatAdamW: no trainable parameters")
         dev = ps[0].device
+        if any(p.device != dev for p in ps):
+            raise RuntimeError("mtlora_b200.FlatAdamW: every parameter must live on the same device (one process per GPU)")
         offs, n = [], 0
         for p in ps:
             offs.append(n)
@@ -92,6 +94,25 @@ class FlatAdamW(torch.optim.Optimizer):
             self.state[p] = {"step": self._state[2 + i], "exp_avg": self._m[offs[i]:offs[i] + p.numel()].view_as(p),
                              "exp_avg_sq": self._v[offs[i]:offs[i] + p.numel()].view_as(p)}
         self._built = True
+
+    def add_param_group(self, param_group):
+        """torch.optim API: parameters added later get fresh (zero) moments; the existing ones keep theirs."""
+        old = None
+        if getattr(self, "_built", False):
+            old = {p: (self._m[o:o + p.numel()].clone(), self._v[o:o + p.numel()].clone(), self._state[2 + i].clone())
+                   for i, (p, o) in enumerate(zip(self._ps, self._offs))}
+            self._built = False
+        super().add_param_group(param_group)
+        if old is not None:
+            if len(self.param_groups) > N.MTL_OPT_MAX_GROUPS:
+                raise ValueError(f"FlatAdamW: at most {N.MTL_OPT_MAX_GROUPS} param groups")
+            self._build()
+            with torch.no_grad():
+                for i, (p, o) in enumerate(zip(self._ps, self._offs)):
+                    if p in old:
+                        self._m[o:o + p.numel()].copy_(old[p][0])
+                        self._v[o:o + p.numel()].copy_(old[p][1])
+                        self._state[2 + i] = old[p][2]
 
     def load_state_dict(self, state_dict):
         if not self._built:

@@ -114,6 +114,28 @@ def test_flat_adamw_state_dict_round_trip(cuda):
         assert torch.equal(x, y)
 
 
+def test_flat_adamw_add_param_group(cuda):
+    """add_param_group after the first step (e.g. unfreezing the decoder heads later): old moments survive."""
+    from mtlora_b200.optim import FlatAdamW
+    a, b = make_params(cuda, 3), make_params(cuda, 3)
+    oa = FlatAdamW(a[:6], lr=1e-2, weight_decay=0.0)
+    ob = torch.optim.AdamW(b[:6], lr=1e-2, weight_decay=0.0)
+    for it in range(2):
+        set_grads(a, it)
+        set_grads(b, it)
+        oa.step()
+        ob.step()
+    oa.add_param_group({"params": a[6:], "weight_decay": 0.0})
+    ob.add_param_group({"params": b[6:], "weight_decay": 0.0})
+    for it in range(2, 4):
+        set_grads(a, it)
+        set_grads(b, it)
+        oa.step()
+        ob.step()
+    for i, (x, y) in enumerate(zip(a, b)):
+        assert torch.allclose(x, y, rtol=3e-6, atol=1e-7), (i, (x - y).abs().max().item())
+
+
 def test_flat_adamw_rejects_cpu():
     from mtlora_b200.optim import FlatAdamW
     p = torch.nn.Parameter(torch.zeros(4))
