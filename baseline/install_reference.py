@@ -4,10 +4,9 @@
 
     python baseline/install_reference.py            # source: $MTLORA_REFERENCE or /root/reference
 
-Copies `models/`, `kernels/`, `configs/`, `mtl_loss_schemes.py`, `optimizer.py` byte for byte (the parts of the reference
-the hot path, its MultiTaskSwin caller and its train step need; `config.py` / `utils.py` / `data/` are left out: they
-import yacs / cv2 / imageio / easydict, which this image does not have) and records a manifest with the sha256 of
-every file. Nothing under `baseline/_ref/` is ever committed (see .gitignore) and the product (`mtlora_b200/`) never
+Copies `models/`, `kernels/`, `configs/`, `mtl_loss_schemes.py`, `optimizer.py`, `main.py`, `utils.py`, `config.py`,
+`logger.py`, `lr_scheduler.py`, `data/`, `evaluation/` byte for byte (the hot path, its MultiTaskSwin caller, its train
+loop and its YAML/config machinery) and records a manifest with the sha256 of every file. Nothing under `baseline/_ref/` is ever committed (see .gitignore) and the product (`mtlora_b200/`) never
 imports it: it is the reference arm of bench.py (`--impl reference-gpu`) and the live comparator of the `-m gpu`
 parity tests. Third-party imports of the reference that are absent here (timm==0.9.2, termcolor, ptflops) are served
 by the tiny stand-ins under `baseline/stubs/`.
@@ -20,7 +19,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 DST = os.path.join(HERE, "_ref")
-ITEMS = ["models", "kernels", "configs", "mtl_loss_schemes.py", "optimizer.py", "LICENSE"]
+ITEMS = ["models", "kernels", "configs", "mtl_loss_schemes.py", "optimizer.py", "LICENSE",
+         # the training script itself, for the drop-in test that runs main.py's own train_one_epoch (its third-party
+         # imports that this image lacks — yacs, timm, easydict, imageio, matplotlib, scikit-image — are served by
+         # baseline/stubs/)
+         "main.py", "utils.py", "config.py", "logger.py", "lr_scheduler.py", "data", "evaluation"]
 
 
 def install(src=None, quiet=False):

@@ -47,6 +47,33 @@ def load():
     return ns
 
 
+def load_main():
+    """The reference's training script and config machinery themselves (main.py, config.py, utils.py, lr_scheduler.py,
+    unmodified): returns a namespace with .config (module), .main (module), .utils, .lr_scheduler, .build (models.build)."""
+    load()
+    with contextlib.redirect_stdout(io.StringIO()):
+        ns = types.SimpleNamespace(config=importlib.import_module("config"), main=importlib.import_module("main"),
+                                   utils=importlib.import_module("utils"),
+                                   lr_scheduler=importlib.import_module("lr_scheduler"),
+                                   build=importlib.import_module("models.build"))
+    return ns
+
+
+def yaml_path(name):
+    """Path of a shipped YAML, e.g. 'mtlora/tiny_448/mtlora_tiny_448_r64_scale4_pertask.yaml'."""
+    return os.path.join(REF, "configs", name)
+
+
+def reference_config(yaml_name, tasks, opts=None, batch_size=None):
+    """config.get_config(args) of the reference for a shipped YAML, exactly as main.py:parse_option builds it
+    (`--cfg <yaml> --pascal <path> --tasks a,b,c [--opts ...]`)."""
+    m = load_main()
+    args = types.SimpleNamespace(cfg=yaml_path(yaml_name), opts=list(opts) if opts else None, tasks=",".join(tasks),
+                                 pascal="/nonexistent/PASCAL_MT", local_rank=0, batch_size=batch_size)
+    with contextlib.redirect_stdout(io.StringIO()):
+        return m.config.get_config(args)
+
+
 class _Node(dict):
     """Minimal attribute-dict standing in for the yacs CfgNode the reference passes around (config.py)."""
     __getattr__ = dict.__getitem__

@@ -62,3 +62,36 @@ def test_multitask_swin_accepts_this_backbone():
     # the reference's optimizer grouping (optimizer.py:62-78) works on it unchanged
     groups = ref.optimizer.set_weight_decay(net, net.backbone.no_weight_decay(), net.backbone.no_weight_decay_keywords())
     assert len(groups) == 2 and sum(len(g["params"]) for g in groups) == len(tr)
+
+
+SHIPPED_YAMLS = ["mtlora_plus_tiny_448_r16_scale4.yaml", "mtlora_plus_tiny_448_r16_scale4_pertask.yaml",
+                 "mtlora_plus_tiny_448_r32_scale4_pertask.yaml", "mtlora_plus_tiny_448_r4_scale4.yaml",
+                 "mtlora_plus_tiny_448_r64_scale4_pertask.yaml", "mtlora_plus_tiny_448_r8_scale4.yaml",
+                 "mtlora_tiny_448_r16_scale4_pertask.yaml", "mtlora_tiny_448_r32_scale4_pertask.yaml",
+                 "mtlora_tiny_448_r64_scale4_pertask.yaml"]
+
+
+@pytest.mark.parametrize("name", SHIPPED_YAMLS)
+def test_every_shipped_yaml_builds_through_the_references_own_factory(name):
+    """YAML surface: the reference's own config.get_config + models.build.build_model / build_mtl_model
+    (models/build.py:19-91), with ONE import swapped as INTEGRATION.md §1 says, construct this repo's backbone for every
+    shipped YAML; parameter names / shapes equal the all-reference model's, and the planner accepts every layer."""
+    from mtlora_b200 import swin_transformer_mtlora as S
+    m = refload.load_main()
+    tasks = ["semseg", "normals", "sal", "human_parts"]
+    config = refload.reference_config("mtlora/tiny_448/" + name, tasks)
+    assert config.MODEL.MTLORA.ENABLED and len(config.MODEL.MTLORA.R_PER_TASK_LIST) == 4
+    with contextlib.redirect_stdout(io.StringIO()):
+        rnet = m.build.build_mtl_model(m.build.build_model(config), config)
+        orig = m.build.SwinTransformerMTLoRA
+        m.build.SwinTransformerMTLoRA = S.SwinTransformerMTLoRA          # <- the one-line swap
+        try:
+            net = m.build.build_mtl_model(m.build.build_model(config), config)
+        finally:
+            m.build.SwinTransformerMTLoRA = orig
+    assert type(net.backbone).__module__.startswith("mtlora_b200")
+    a = {n: tuple(p.shape) for n, p in rnet.named_parameters()}
+    b = {n: tuple(p.shape) for n, p in net.named_parameters()}
+    assert list(a) == list(b) and a == b
+    plus = config.MODEL.MTLORA.DOWNSAMPLER_ENABLED
+    assert ("backbone.layers.0.downsample.reduction.lora_shared_A" in b) == bool(plus)

@@ -490,3 +490,58 @@ def test_drop_path_draws(S):
     assert off.abs().max().item() < 5 / B ** 0.5          # the six (branch, stream) draws are independent
     blk.eval()
     assert blk.path_scales(8, 3, torch.device("cuda")) == (None, None)
+
+
+def test_reference_train_one_epoch_runs_unmodified(S):
+    """north_star: "drops into main.py's torch.distributed loop unchanged". The reference's OWN code — config.get_config on
+    the shipped YAML, models.build.build_model / build_mtl_model, mark_only_lora_as_trainable, optimizer.build_optimizer,
+    lr_scheduler.build_scheduler, utils.NativeScalerWithGradNormCount and main.train_one_epoch (main.py:309-427: fp16
+    autocast, GradScaler, clip_grad_norm_, AdamW, lr schedule, meters) — runs over this repo's backbone with ONE import
+    swapped, on a synthetic PASCAL-shaped loader, and trains the adapters."""
+    import logging
+    from baseline import refload
+    if not refload.available() or not os.path.exists(os.path.join(refload.REF, "main.py")):
+        pytest.skip("baseline/_ref (with main.py) not installed")
+    m = refload.load_main()
+    tasks = TASKS6[:4]
+    config = refload.reference_config("mtlora/tiny_448/mtlora_tiny_448_r64_scale4_pertask.yaml", tasks,
+                                      opts=["DATA.IMG_SIZE", 224, "TRAIN.EPOCHS", 1, "TRAIN.WARMUP_EPOCHS", 0, "PRINT_FREQ", 1])
+    orig = m.build.SwinTransformerMTLoRA
+    m.build.SwinTransformerMTLoRA = S.SwinTransformerMTLoRA          # <- the one-line swap of INTEGRATION.md
+    try:
+        torch.manual_seed(0)
+        model = quiet(lambda: m.build.build_mtl_model(m.build.build_model(config), config))
+    finally:
+        m.build.SwinTransformerMTLoRA = orig
+    assert type(model.backbone).__module__.startswith("mtlora_b200")
+    with torch.no_grad():     # non-zero adapters, like a run that has trained for a while
+        g = torch.Generator().manual_seed(1)
+        for n, p in model.named_parameters():
+            if "lora_shared_B" in n or "lora_tasks_B" in n:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    model.cuda()
+    quiet(m.main.mark_only_lora_as_trainable, model.backbone, bias=config.MODEL.MTLORA.BIAS,
+          freeze_patch_embed=config.TRAIN.FREEZE_PATCH_EMBED, freeze_norm=config.TRAIN.FREEZE_LAYER_NORM,
+          free_relative_bias=config.TRAIN.FREEZE_RELATIVE_POSITION_BIAS,
+          freeze_downsample_reduction=True if config.MODEL.MTLORA.DOWNSAMPLER_ENABLED else config.TRAIN.FREEZE_DOWNSAMPLE_REDUCTION)
+    optimizer = m.main.build_optimizer(config, model)
+    loss_scaler = m.main.NativeScalerWithGradNormCount()
+    gen = torch.Generator().manual_seed(7)
+    loader = []
+    for _ in range(3):
+        batch = {"image": torch.randn(2, 3, 224, 224, generator=gen)}
+        batch.update(refload.synthetic_targets(tasks, 2, 224, gen))
+        loader.append(batch)
+    lr_scheduler = m.main.build_scheduler(config, optimizer, len(loader))
+    loss_ft = torch.nn.ModuleDict({t: m.main.get_loss(config["TASKS_CONFIG"], t, config) for t in tasks})
+    criterion = m.main.MultiTaskLoss(tasks, loss_ft, {t: refload.LOSS_WEIGHTS[t] for t in tasks})
+    m.main.logger = logging.getLogger("mtlora_b200.test")     # main.py creates it under __main__
+    m.main.wandb_available = False
+    before = {n: p.detach().clone() for n, p in model.named_parameters() if p.requires_grad}
+    m.main.train_one_epoch(config, model, criterion, loader, optimizer, 0, None, lr_scheduler, loss_scaler)
+    torch.cuda.synchronize()
+    changed = [n for n, p in model.named_parameters() if p.requires_grad and not torch.equal(p.detach(), before[n])]
+    assert any("lora_shared_A" in n for n in changed) and any("lora_tasks_B" in n for n in changed)
+    assert any(n.startswith("decoders") for n in changed)
+    assert all(torch.isfinite(p).all() for p in model.parameters())
+    assert loss_scaler.state_dict()["scale"] > 0
