@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MTL_ABI_VERSION 2
+#define MTL_ABI_VERSION 3
 #define MTL_MAX_TASKS 7
 
 typedef void* mtl_stream_t; /* cudaStream_t */
@@ -83,6 +83,23 @@ int mtl_linear_rank_offset(const mtl_linear_cfg* cfg, int idx);
 int mtl_linear_pack(const mtl_linear_cfg* cfg, const float* a_shared, const float* b_shared,
                     const float* const* a_tasks, const float* const* b_tasks, void* a_cat, void* b_cat,
                     void* a_cat_t, void* b_cat_t, mtl_stream_t stream);
+
+/* mtl_linear_pack for many layers in ONE launch: the adapters of every layer change once per optimizer step, and ~50
+ * launches of a few microseconds each add up (reference: none — models/lora.py:253-284 reads the fp32 parameters directly;
+ * this is the operand staging of the bf16 kernels). Any of the four outputs of a job may be NULL. */
+typedef struct mtl_pack_job {
+  mtl_linear_cfg cfg;                       /* in_features, out_features, n_tasks, r_shared, r_task */
+  const float* a_shared;                    /* [r_shared, in] */
+  const float* b_shared;                    /* [out, r_shared] */
+  const float* a_tasks[MTL_MAX_TASKS];      /* [r_task[t], in] */
+  const float* b_tasks[MTL_MAX_TASKS];      /* [out, r_task[t]] */
+  void* a_cat;                              /* bf16 [R, in] */
+  void* b_cat;                              /* bf16 [out, R] */
+  void* a_cat_t;                            /* bf16 [in, R] */
+  void* b_cat_t;                            /* bf16 [R, out] */
+} mtl_pack_job;
+int mtl_pack_job_size(void);
+int mtl_linear_pack_many(const mtl_pack_job* jobs, int32_t n_jobs, mtl_stream_t stream);
 
 /* Rank-space projection of a layer without task adapters (lora.py:260: the `x @ A^T` half of the shared update) as a
  * launch of its own, for the compute-bound layers of stages 2-3:

@@ -7,7 +7,7 @@ import ctypes
 import os
 
 MTL_MAX_TASKS = 7
-MTL_ABI_VERSION = 2
+MTL_ABI_VERSION = 3
 MTL_MODE_MATRIX, MTL_MODE_MATRIXV2 = 0, 1
 MTL_ACT_NONE, MTL_ACT_GELU, MTL_ACT_GELU_GRAD = 0, 1, 2
 
@@ -58,6 +58,13 @@ class OptGroup(ctypes.Structure):
     _fields_ = [("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("weight_decay", c_float)]
 
 
+class PackJob(ctypes.Structure):
+    """mtl_pack_job: operand staging of one layer inside mtl_linear_pack_many."""
+    _fields_ = [("cfg", LinearCfg), ("a_shared", c_void_p), ("b_shared", c_void_p),
+                ("a_tasks", c_void_p * MTL_MAX_TASKS), ("b_tasks", c_void_p * MTL_MAX_TASKS),
+                ("a_cat", c_void_p), ("b_cat", c_void_p), ("a_cat_t", c_void_p), ("b_cat_t", c_void_p)]
+
+
 MTL_OPT_CHUNK, MTL_OPT_MAX_GROUPS = 4096, 8
 _CFG_P = ctypes.POINTER(LinearCfg)
 _PP = ctypes.POINTER(c_void_p)
@@ -71,6 +78,8 @@ SIGNATURES = {
     "mtl_linear_rank_pad": (c_int, [_CFG_P]),
     "mtl_linear_rank_offset": (c_int, [_CFG_P, c_int]),
     "mtl_linear_pack": (c_int, [_CFG_P, c_void_p, c_void_p, _PP, _PP, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mtl_pack_job_size": (c_int, []),
+    "mtl_linear_pack_many": (c_int, [ctypes.POINTER(PackJob), c_int32, c_void_p]),
     "mtl_cast_transpose": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "mtl_linear_rank_project": (c_int, [_CFG_P, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mtl_linear_fwd": (c_int, [_CFG_P, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
@@ -133,6 +142,8 @@ def load():
     if lib.mtl_linear_cfg_size() != ctypes.sizeof(LinearCfg):
         raise RuntimeError(f"struct mtl_linear_cfg is {lib.mtl_linear_cfg_size()} bytes in libmtlora_b200.so but "
                            f"{ctypes.sizeof(LinearCfg)} in the ctypes mirror; rebuild (`make`)")
+    if lib.mtl_pack_job_size() != ctypes.sizeof(PackJob):
+        raise RuntimeError("struct mtl_pack_job differs between libmtlora_b200.so and the ctypes mirror; rebuild (`make`)")
     _lib = lib
     return lib
 

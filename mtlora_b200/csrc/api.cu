@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <atomic>
 #include <string.h>
+#include <vector>
 
 #include "kernels.cuh"
 #include "linear_sm100.cuh"
@@ -184,6 +185,40 @@ int mtl_linear_pack(const mtl_linear_cfg* cfg, const float* a_shared, const floa
   }
   return launch_pack_adapters(ap, bp, L.rank, L.off, L.n, cfg->in_features, cfg->out_features, L.R_pad, a_cat, b_cat,
                               a_cat_t, b_cat_t, S(stream));
+}
+
+int mtl_pack_job_size(void) { return static_cast<int>(sizeof(mtl_pack_job)); }
+
+int mtl_linear_pack_many(const mtl_pack_job* jobs, int32_t n_jobs, mtl_stream_t stream) {
+  MTL_REQUIRE(n_jobs >= 0 && (n_jobs == 0 || jobs != nullptr), "linear_pack_many: bad job list");
+  if (n_jobs == 0) return 0;
+  std::vector<PackJobHost> hs(static_cast<size_t>(n_jobs));
+  for (int j = 0; j < n_jobs; ++j) {
+    const mtl_pack_job& jb = jobs[j];
+    RankLayout L;
+    if (int e = build_layout(&jb.cfg, &L)) return e;
+    MTL_REQUIRE(L.n > 0, "linear_pack_many: job %d has no adapters (r_shared == 0)", j);
+    MTL_REQUIRE(jb.a_shared != nullptr && jb.b_shared != nullptr, "linear_pack_many: job %d: shared adapter pointers are NULL", j);
+    PackJobHost& h = hs[j];
+    memset(&h, 0, sizeof(h));
+    h.a[0] = jb.a_shared;
+    h.b[0] = jb.b_shared;
+    for (int t = 0; t < jb.cfg.n_tasks; ++t) {
+      MTL_REQUIRE(jb.a_tasks[t] != nullptr && jb.b_tasks[t] != nullptr, "linear_pack_many: job %d: task %d adapter pointer is NULL", j, t);
+      h.a[1 + t] = jb.a_tasks[t];
+      h.b[1 + t] = jb.b_tasks[t];
+    }
+    for (int i = 0; i < L.n; ++i) {
+      h.rank[i] = L.rank[i];
+      h.off[i] = L.off[i];
+    }
+    h.n_adapt = L.n;
+    h.K = jb.cfg.in_features;
+    h.N = jb.cfg.out_features;
+    h.R_pad = L.R_pad;
+    h.a_cat = jb.a_cat; h.b_cat = jb.b_cat; h.a_cat_t = jb.a_cat_t; h.b_cat_t = jb.b_cat_t;
+  }
+  return launch_pack_adapters_many(hs.data(), n_jobs, S(stream));
 }
 
 int mtl_linear_rank_project(const mtl_linear_cfg* cfg, int32_t pass, const void* x, const void* down, void* u_out,

@@ -55,6 +55,15 @@ int launch_add(const void* a, const void* b, void* out, long n, cudaStream_t str
 int launch_pack_adapters(const float* const* a_ptrs, const float* const* b_ptrs, const int* ranks, const int* offs,
                          int n_adapt, int K, int N, int R_pad, void* a_cat, void* b_cat, void* a_cat_t, void* b_cat_t,
                          cudaStream_t stream);
+// One launch for the packed operands of many layers (mtl_linear_pack_many).
+struct PackJobHost {
+  const float* a[8];
+  const float* b[8];
+  int rank[8], off[8];
+  int n_adapt, K, N, R_pad;
+  void *a_cat, *b_cat, *a_cat_t, *b_cat_t;
+};
+int launch_pack_adapters_many(const PackJobHost* jobs, int n_jobs, cudaStream_t stream);
 // fp32 [rows, cols] -> bf16 copy and/or bf16 transposed copy
 int launch_cast_transpose(const float* w, void* w_bf16, void* wt_bf16, int rows, int cols, cudaStream_t stream);
 

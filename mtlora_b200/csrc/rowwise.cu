@@ -661,10 +661,10 @@ struct PackParams {
 };
 
 // a_cat [R_pad, K], b_cat [N, R_pad], a_cat_t [K, R_pad], b_cat_t [R_pad, N]; zero padded.
-__global__ void pack_adapters_kernel(const PackParams p) {
+// Elements start, start + stride, ... of one layer's packed operands.
+__device__ __forceinline__ void pack_adapters_body(const PackParams& p, long start, long stride) {
   const long nA = static_cast<long>(p.R_pad) * p.K, nB = static_cast<long>(p.N) * p.R_pad;
-  for (long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < nA + nB;
-       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+  for (long idx = start; idx < nA + nB; idx += stride) {
     if (idx < nA) {
       const int r = static_cast<int>(idx / p.K), k = static_cast<int>(idx - static_cast<long>(r) * p.K);
       float v = 0.f;
@@ -684,6 +684,30 @@ __global__ void pack_adapters_kernel(const PackParams p) {
       if (p.b_cat_t) p.b_cat_t[static_cast<long>(r) * p.N + n] = h;
     }
   }
+}
+
+__global__ void pack_adapters_kernel(const PackParams p) {
+  pack_adapters_body(p, static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long>(gridDim.x) * blockDim.x);
+}
+
+// All layers of a model in ONE launch (the adapters change once per optimizer step: 48 launches of ~6 us otherwise).
+// The job table travels as a kernel parameter (<= 32 KiB on sm_100); blocks [blk0[j], blk0[j + 1]) serve job j.
+constexpr int kPackManyMax = 64;
+struct PackMany {
+  int n;
+  int blk0[kPackManyMax + 1];
+  PackParams job[kPackManyMax];
+};
+static_assert(sizeof(PackMany) <= 32 * 1024 - 64, "job table exceeds the kernel parameter space");
+
+__global__ void pack_adapters_many_kernel(const __grid_constant__ PackMany pm) {
+  int lo = 0, hi = pm.n;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (pm.blk0[mid] <= static_cast<int>(blockIdx.x)) lo = mid; else hi = mid;
+  }
+  const int blk = blockIdx.x - pm.blk0[lo], n_blk = pm.blk0[lo + 1] - pm.blk0[lo];
+  pack_adapters_body(pm.job[lo], static_cast<long>(blk) * blockDim.x + threadIdx.x, static_cast<long>(n_blk) * blockDim.x);
 }
 
 __global__ void cast_transpose_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wb,
@@ -887,6 +911,40 @@ int launch_pack_adapters(const float* const* a_ptrs, const float* const* b_ptrs,
   const long total = static_cast<long>(R_pad) * (K + N);
   pack_adapters_kernel<<<grid_for(total, 256), 256, 0, stream>>>(p); note_launch();
   MTL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_pack_adapters_many(const PackJobHost* jobs, int n_jobs, cudaStream_t stream) {
+  for (int j0 = 0; j0 < n_jobs; j0 += kPackManyMax) {
+    static thread_local PackMany pm;   // 15 KiB: keep it off the stack
+    pm.n = n_jobs - j0 < kPackManyMax ? n_jobs - j0 : kPackManyMax;
+    int blocks = 0;
+    for (int j = 0; j < pm.n; ++j) {
+      const PackJobHost& h = jobs[j0 + j];
+      MTL_REQUIRE(h.n_adapt >= 1 && h.n_adapt <= 8, "pack_many: job %d: adapter count %d out of range", j0 + j, h.n_adapt);
+      PackParams& p = pm.job[j];
+      for (int i = 0; i < 8; ++i) {
+        p.a[i] = i < h.n_adapt ? h.a[i] : nullptr;
+        p.b[i] = i < h.n_adapt ? h.b[i] : nullptr;
+        p.rank[i] = i < h.n_adapt ? h.rank[i] : 0;
+        p.off[i] = i < h.n_adapt ? h.off[i] : 0;
+        if (i < h.n_adapt) MTL_REQUIRE(h.off[i] + h.rank[i] <= h.R_pad, "pack_many: job %d: adapter %d exceeds R_pad", j0 + j, i);
+      }
+      p.n = h.n_adapt; p.K = h.K; p.N = h.N; p.R_pad = h.R_pad;
+      p.a_cat = static_cast<__nv_bfloat16*>(h.a_cat);
+      p.b_cat = static_cast<__nv_bfloat16*>(h.b_cat);
+      p.a_cat_t = static_cast<__nv_bfloat16*>(h.a_cat_t);
+      p.b_cat_t = static_cast<__nv_bfloat16*>(h.b_cat_t);
+      const long total = static_cast<long>(h.R_pad) * (h.K + h.N);
+      long nb = (total + 1023) / 1024;   // ~4 elements per thread
+      if (nb > 128) nb = 128;
+      pm.blk0[j] = blocks;
+      blocks += static_cast<int>(nb);
+    }
+    pm.blk0[pm.n] = blocks;
+    pack_adapters_many_kernel<<<blocks, 256, 0, stream>>>(pm); note_launch();
+    MTL_CHECK_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 

@@ -7,6 +7,7 @@ libmtlora_b200.so (`mtl_linear_fwd` / `mtl_linear_bwd_input` / `mtl_linear_bwd_p
 bf16 with fp32 accumulation. There is no PyTorch fallback: CPU tensors raise.
 """
 import math
+import os
 from typing import Any, Dict, Mapping, Optional, Union
 
 import torch
@@ -15,6 +16,9 @@ import torch.nn as nn
 from . import ops
 
 BF16 = torch.bfloat16
+# input-gradient width (in_features) above which a multi-stream layer takes the stream sum of dy appended in place by
+# its caller (LinearEngine.backward, dy_full): 128 = one column chunk; tuning aid
+SUM_IN_PLACE_MIN_K = int(os.environ.get("MTL_SUM_IN_PLACE_MIN_K", "128"))
 
 
 class LoRALayer(nn.Module):
@@ -96,6 +100,23 @@ class LinearEngine:
         return ([lin.weight] + ([lin.bias] if lin.bias is not None else [])
                 + [p for p in self.adapters() if isinstance(p, nn.Parameter)] + [p for _, p in self.scales()])
 
+    def _adapter_key(self):
+        ad = self.adapters()
+        sc = self.scales()
+        return ad, sc, tuple((p.data_ptr(), p._version) for p in ad + [q for _, q in sc])
+
+    def pack_job(self):
+        """(spec, a_shared, b_shared, a_tasks, b_tasks) when the packed adapter operands are stale and can be staged by
+        `stage_many` (no trainable scale to fold in), else None."""
+        if self.spec.r_shared == 0:
+            return None
+        ad, sc, akey = self._adapter_key()
+        if akey == self._akey or sc or any(p.dtype != torch.float32 or not p.is_contiguous() or not p.is_cuda for p in ad):
+            return None
+        T = len(self.tasks)
+        return akey, (self.spec, ad[0].detach(), ad[1].detach(), [p.detach() for p in ad[2:2 + T]],
+                      [p.detach() for p in ad[2 + T:2 + 2 * T]])
+
     def stage(self):
         w = self.linear.weight
         if not w.is_cuda:
@@ -141,11 +162,14 @@ class LinearEngine:
                          rows_per_sample=rows_per_sample, staged=staged)
         return y, y_act, saved
 
-    def backward(self, saved, dy, *, gelu_aux=None, aux_is_grad=False, need_dx=True):
+    def backward(self, saved, dy, *, gelu_aux=None, aux_is_grad=False, need_dx=True, dy_full=None, dx_spare=False):
         """dy [S_out, M, N] -> dx [1 (+T), M, K], {param: fp32 grad} for every parameter that requires grad.
 
         DropPath (`path_scale` given in forward): a single-stream layer scales inside the kernels, a multi-stream
-        layer pre-scales dy once (header contract of mtl_linear_bwd_input)."""
+        layer pre-scales dy once (header contract of mtl_linear_bwd_input).
+        dx_spare: dx comes back as [1 (+T) + 1, M, K] with a free last stream. dy_full: such a buffer whose leading
+        streams ARE `dy` — the stream sum the frozen product needs is then appended in place (one read of dy, one
+        stream written) instead of re-streaming all 1+T operand tiles for every column chunk."""
         spec = self.spec
         _, wt, (_, _, a_cat_t, b_cat_t) = saved.get("staged") or self.stage()
         ps, rps = saved["path_scale"], saved["rows_per_sample"]
@@ -157,6 +181,11 @@ class LinearEngine:
             # DropPath pre-scale pass is needed anyway (it writes the sum along)
             dy_in = ops.scale_rows_sum(dy, ps, rps)
             dy, dy_sum, ps = dy_in[:spec.S_out], True, None
+        elif (dy_full is not None and 1 < spec.S_out < 8 and ps is None and spec.K > SUM_IN_PLACE_MIN_K
+              and dy_full.shape[0] == spec.S_out + 1 and dy_full.data_ptr() == dy.data_ptr()):
+            # fc1 of a multi-stream block (K = C outputs of the input gradient in 2+ column chunks): see dy_full above
+            ops.sum_streams(dy, out=dy_full[spec.S_out])
+            dy_in, dy_sum = dy_full, True
         elif ps is not None and spec.S_out > 1:
             dy = dy_in = ops.scale_rows(dy, ps, rps)
             ps = None
@@ -166,7 +195,8 @@ class LinearEngine:
         dx, g = ops.linear_bwd_input(spec, dy_in, wt, a_cat_t, b_cat_t, x_tasks_given=saved["xt"], gelu_aux=gelu_aux,
                                      aux_is_grad=aux_is_grad, dy_has_sum=dy_sum,
                                      path_scale=ps, rows_per_sample=rps if ps is not None else 0,
-                                     dropout_p=saved["dropout_p"], seed=saved["seed"], save_g=want_ad)
+                                     dropout_p=saved["dropout_p"], seed=saved["seed"], save_g=want_ad,
+                                     spare_stream=dx_spare)
         grads = {}
         if want_ad:
             da, db = ops.linear_bwd_params(spec, saved["x"], dy_in if (v2 and dy_sum) else dy, saved["u"], g,
@@ -203,6 +233,26 @@ class LinearEngine:
                 ones = torch.ones((M, 8), dtype=BF16, device=dy.device)
                 grads[lin.bias] = ops.xty(dpre, ones)[:, 0]
         return dx, grads
+
+
+def stage_many(engines):
+    """Refresh the packed bf16 adapter operands of every engine whose fp32 masters changed (one optimizer step = all of
+    them) in ONE launch instead of one per layer; `LinearEngine.stage` then finds them current."""
+    todo = []
+    for e in engines:
+        j = e.pack_job()
+        if j is not None:
+            todo.append((e, j[0], j[1]))
+    if len(todo) < 2:
+        return 0          # a single stale layer: its own stage() handles it
+    dev = todo[0][2][1].device
+    if any(t[2][1].device != dev for t in todo):
+        return 0
+    with torch.no_grad():
+        packed = ops.pack_adapters_many([t[2] for t in todo])
+    for (e, akey, _), pk in zip(todo, packed):
+        e._packed, e._akey = pk, akey
+    return len(todo)
 
 
 class _LinearFn(torch.autograd.Function):

@@ -158,6 +158,44 @@ def pack_adapters(spec, a_shared, b_shared, a_tasks=(), b_tasks=(), fwd=True, bw
     return a_cat, b_cat, a_cat_t, b_cat_t
 
 
+def pack_adapters_many(jobs):
+    """pack_adapters for many layers in ONE launch (mtl_linear_pack_many). jobs: [(spec, a_shared, b_shared, a_tasks,
+    b_tasks)] of fp32 CUDA tensors on one device -> [(a_cat, b_cat, a_cat_t, b_cat_t)] in job order; the packed operands
+    are views of one freshly allocated bf16 buffer."""
+    if not jobs:
+        return []
+    dev = jobs[0][1].device
+    sizes = [2 * spec.R_pad * (spec.K + spec.Nf) for spec, *_ in jobs]
+    offs, n = [], 0
+    for sz in sizes:
+        offs.append(n)
+        n += (sz + 7) // 8 * 8          # every operand stays 16-byte aligned (R_pad * K and N * R_pad are multiples of 8)
+    buf = torch.empty(n, dtype=BF16, device=dev)
+    arr = (N.PackJob * len(jobs))()
+    out = []
+    for j, (spec, a_s, b_s, a_t, b_t) in enumerate(jobs):
+        for i, t in enumerate([a_s, b_s, *a_t, *b_t]):
+            _chk(t, torch.float32, f"job {j}: adapter[{i}]")
+        if len(a_t) != spec.T or len(b_t) != spec.T:
+            raise ValueError(f"pack_adapters_many: job {j} needs {spec.T} task adapters")
+        R, K, Nf = spec.R_pad, spec.K, spec.Nf
+        o = offs[j]
+        a_cat = buf[o:o + R * K].view(R, K)
+        b_cat = buf[o + R * K:o + R * (K + Nf)].view(Nf, R)
+        a_cat_t = buf[o + R * (K + Nf):o + R * (2 * K + Nf)].view(K, R)
+        b_cat_t = buf[o + R * (2 * K + Nf):o + 2 * R * (K + Nf)].view(R, Nf)
+        jb = arr[j]
+        jb.cfg = spec.cfg(1, False)
+        jb.a_shared, jb.b_shared = a_s.data_ptr(), b_s.data_ptr()
+        for t in range(spec.T):
+            jb.a_tasks[t], jb.b_tasks[t] = a_t[t].data_ptr(), b_t[t].data_ptr()
+        jb.a_cat, jb.b_cat, jb.a_cat_t, jb.b_cat_t = (a_cat.data_ptr(), b_cat.data_ptr(), a_cat_t.data_ptr(),
+                                                      b_cat_t.data_ptr())
+        out.append((a_cat, b_cat, a_cat_t, b_cat_t))
+    N.call("mtl_linear_pack_many", arr, len(jobs), N.stream())
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # MTLoRALinear
 # ----------------------------------------------------------------------------------------------------------------
@@ -196,9 +234,11 @@ def linear_fwd(spec, x, w_bf16, bias, a_cat, b_cat, *, x_tasks_given=False, act_
 
 
 def linear_bwd_input(spec, dy, wt_bf16, a_cat_t, b_cat_t, *, x_tasks_given=False, gelu_aux=None, aux_is_grad=False,
-                     dy_has_sum=False, path_scale=None, rows_per_sample=0, dropout_p=0.0, seed=0, save_g=False):
+                     dy_has_sum=False, path_scale=None, rows_per_sample=0, dropout_p=0.0, seed=0, save_g=False,
+                     spare_stream=False):
     """dy: [S_out, M, N] (dy_has_sum: [S_out + 1, M, N], last stream = sum of the others, see scale_rows_sum)
-    -> dx [1 (+T), M, K], g_save [M, R] or None."""
+    -> dx [1 (+T), M, K], g_save [M, R] or None. spare_stream: dx is returned as [1 (+T) + 1, M, K] with an unwritten
+    last stream, for a consumer that wants to append the stream sum in place (LinearEngine.backward, dy_full)."""
     _chk(dy, BF16, "dy"); _chk(wt_bf16, BF16, "wt_bf16"); _chk(gelu_aux, BF16, "gelu_aux")
     S, M, Nf = dy.shape
     if dy_has_sum:
@@ -206,7 +246,9 @@ def linear_bwd_input(spec, dy, wt_bf16, a_cat_t, b_cat_t, *, x_tasks_given=False
     if S != spec.S_out or Nf != spec.Nf:
         raise ValueError(f"linear_bwd_input: dy shape {tuple(dy.shape)} does not match the layer ({spec.S_out}, M, {spec.Nf})")
     xt = x_tasks_given and spec.T > 0
-    dx = torch.empty((1 + (spec.T if xt else 0), M, spec.K), dtype=BF16, device=dy.device)
+    n_dx = 1 + (spec.T if xt else 0)
+    dx_full = torch.empty((n_dx + (1 if spare_stream else 0), M, spec.K), dtype=BF16, device=dy.device)
+    dx = dx_full[:n_dx]
     pre = spec.pre_project(M) and not dy_has_sum
     g = torch.empty((M, spec.R_pad), dtype=BF16, device=dy.device) if ((save_g or pre) and spec.r_shared > 0) else None
     c = spec.cfg(M, x_tasks_given, dropout_p, seed, rows_per_sample, gelu_aux_is_grad=aux_is_grad, dy_has_sum=dy_has_sum,
@@ -216,7 +258,7 @@ def linear_bwd_input(spec, dy, wt_bf16, a_cat_t, b_cat_t, *, x_tasks_given=False
     N.call("mtl_linear_bwd_input", ctypes.byref(c), N.ptr(dy), N.ptr(wt_bf16), N.ptr(a_cat_t), N.ptr(b_cat_t),
            N.ptr(dx), N.ptr(gelu_aux), N.ptr(path_scale), N.ptr(g), N.stream(),
            meta=("bwd_input", M, spec.K, spec.Nf, dx.shape[0], S, spec.R_pad, sum(spec.ranks), False))
-    return dx, g
+    return dx_full, g
 
 
 def linear_bwd_params(spec, x, dy, u_save, g_save, *, x_tasks_given=False, x_gelu=False, path_scale=None,
@@ -406,9 +448,12 @@ def add(a, b):
     return out
 
 
-def sum_streams(x, extra=None):
-    """x [S, ...] -> sum over S (+ extra)."""
-    _chk(x, BF16, "x"); _chk(extra, BF16, "extra")
-    out = torch.empty(x.shape[1:], dtype=BF16, device=x.device)
+def sum_streams(x, extra=None, out=None):
+    """x [S, ...] -> sum over S (+ extra), into `out` when given."""
+    _chk(x, BF16, "x"); _chk(extra, BF16, "extra"); _chk(out, BF16, "out")
+    if out is None:
+        out = torch.empty(x.shape[1:], dtype=BF16, device=x.device)
+    elif out.shape != x.shape[1:]:
+        raise ValueError(f"sum_streams: out has shape {tuple(out.shape)}, expected {tuple(x.shape[1:])}")
     N.call("mtl_sum_streams", N.ptr(x), N.ptr(extra), N.ptr(out), x.shape[0], out.numel(), N.stream())
     return out

@@ -19,7 +19,7 @@ import torch.nn as nn
 from torch import Tensor
 
 from . import ops
-from .lora import LinearEngine, MTLoRALinear, _new_seed, run_linear_standalone
+from .lora import LinearEngine, MTLoRALinear, _new_seed, run_linear_standalone, stage_many
 
 BF16 = torch.bfloat16
 
@@ -446,7 +446,9 @@ class _BlockFn(torch.autograd.Function):
         dy = _grad_stack(dys, (M, C), sv["x"].device)
         grads = {}
         # fc2 -> d(fc1 pre-activation), GELU' fused into the epilogue
-        dg, g2 = e_fc2.backward(sv["sv_2"], dy, gelu_aux=sv["g"], aux_is_grad=True)
+        # (multi-stream block: one spare stream behind d(fc1 out), where fc1's backward may append the stream sum)
+        dg_full, g2 = e_fc2.backward(sv["sv_2"], dy, gelu_aux=sv["g"], aux_is_grad=True, dx_spare=S > 1)
+        dg = dg_full[:S] if S > 1 else dg_full
         grads.update(g2)
         dead = []   # parameters that feed ONLY output streams nobody used: autograd reports None for them, not zeros
         if S > 1 and e_fc2.spec.r_shared > 0 and e_fc2.spec.mode == ops.N.MTL_MODE_MATRIX:
@@ -466,9 +468,9 @@ class _BlockFn(torch.autograd.Function):
                         ts = getattr(lay, "lora_task_scale", None)
                         if isinstance(ts, nn.ParameterDict):
                             dead.append(ts[t])
-        dh2, g1 = e_fc1.backward(sv["sv_1"], dg)
+        dh2, g1 = e_fc1.backward(sv["sv_1"], dg, dy_full=dg_full if S > 1 else None)
         grads.update(g1)
-        del dg
+        del dg, dg_full
         n2 = blk.norm2
         want_n2 = n2.weight.requires_grad or n2.bias.requires_grad
         dx1, dw2, db2 = ops.layernorm_bwd(dh2.view(S * M, C), sv["x1"].view(S * M, C), sv["n2w"], sv["mean2"],
@@ -1060,9 +1062,19 @@ class SwinTransformerMTLoRA(nn.Module):
         if gs is not None:
             self.__dict__.setdefault("_grad_syncs", []).append(gs)
 
+    def _stage_adapters(self):
+        """Re-pack the bf16 adapter operands of all layers in one launch when an optimizer step changed them."""
+        mods = self.__dict__.get("_lin_modules")
+        if mods is None:
+            mods = [m for m in self.modules() if m is not self and hasattr(type(m), "engine")]
+            self.__dict__["_lin_modules"] = mods
+        stage_many([m.engine for m in mods])
+
     def forward_features(self, x, return_stages=False, flatten_ft=False):
         if self.training and torch.is_grad_enabled():
             self._attach_grad_sync()
+        if x.is_cuda:
+            self._stage_adapters()
         x = self.patch_embed(x)
         if self.ape:
             x = x + self.absolute_pos_embed

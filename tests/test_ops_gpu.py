@@ -92,6 +92,46 @@ def test_pack_adapters_exact(ops):
     assert torch.equal(a_cat_t, bf(ref_a).t().contiguous()) and torch.equal(b_cat_t, bf(ref_b).t().contiguous())
 
 
+def test_pack_adapters_many_matches_single(ops):
+    """mtl_linear_pack_many (all layers in one launch) == mtl_linear_pack per layer, bit for bit."""
+    layers = [make_layer(ops, "pm0", 96, 288, 64, []), make_layer(ops, "pm1", 96, 384, 64, [4, 4, 4, 4]),
+              make_layer(ops, "pm2", 768, 192, 20, [4, 7]), make_layer(ops, "pm3", 1536, 384, 16, [])]
+    jobs = [(spec, p["lora_shared_A"], p["lora_shared_B"], [p["lora_tasks_A." + t] for t in tasks],
+             [p["lora_tasks_B." + t] for t in tasks]) for spec, p, tasks, _ in layers]
+    many = ops.pack_adapters_many(jobs)
+    assert len(many) == len(layers)
+    for (spec, p, tasks, _), got in zip(layers, many):
+        want = pack(ops, spec, p, tasks)[2:]
+        for g, w in zip(got, want):
+            assert g.shape == w.shape and g.data_ptr() % 16 == 0 and torch.equal(g, w)
+    assert ops.pack_adapters_many([]) == []
+    # more jobs than one launch carries (64)
+    big = ops.pack_adapters_many(jobs * 20)
+    for k, got in enumerate(big):
+        want = many[k % len(jobs)]
+        assert all(torch.equal(g, w) for g, w in zip(got, want))
+
+
+def test_linear_bwd_input_sum_appended_in_place(ops):
+    """spare_stream / sum_streams(out=): the producer leaves one free stream behind its result, the consumer appends
+    the stream sum there and runs with dy_has_sum — same dx as the (1+T)-stream form."""
+    M, K, N, T = 784, 192, 768, 4
+    spec, p, tasks, _ = make_layer(ops, "sip", K, N, 64, [4] * T)
+    _, wt, _, _, a_cat_t, b_cat_t = pack(ops, spec, p, tasks)
+    full = torch.empty((1 + T + 1, M, N), dtype=torch.bfloat16, device="cuda")
+    full[:1 + T] = bf(dev(detgen.uniform("sip.dy", (1 + T, M, N))))
+    dy = full[:1 + T]
+    ops.sum_streams(dy, out=full[1 + T])
+    check(full[1 + T], dy.float().sum(0), what="stream sum")
+    dx_a, g_a = ops.linear_bwd_input(spec, full, wt, a_cat_t, b_cat_t, x_tasks_given=True, dy_has_sum=True, save_g=True)
+    dx_b, g_b = ops.linear_bwd_input(spec, dy, wt, a_cat_t, b_cat_t, x_tasks_given=True, save_g=True, spare_stream=True)
+    assert dx_b.shape == (1 + T + 1, M, K) and dx_a.shape == (1 + T, M, K)
+    check(dx_a, dx_b[:1 + T].float(), what="dx with the sum appended vs streams")
+    assert torch.equal(g_a, g_b)
+    with pytest.raises(ValueError):
+        ops.sum_streams(dy, out=full[0, :10])
+
+
 LINEAR_CASES = [
     # tag,        M,     K,    N,   r_s, r_t,          xt,    gelu,  res,  pscale
     ("dense",     300,   96,   288, 0,   [],           False, False, 0,    False),
