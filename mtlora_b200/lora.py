@@ -105,18 +105,6 @@ class LinearEngine:
         sc = self.scales()
         return ad, sc, tuple((p.data_ptr(), p._version) for p in ad + [q for _, q in sc])
 
-    def pack_job(self):
-        """(spec, a_shared, b_shared, a_tasks, b_tasks) when the packed adapter operands are stale and can be staged by
-        `stage_many` (no trainable scale to fold in), else None."""
-        if self.spec.r_shared == 0:
-            return None
-        ad, sc, akey = self._adapter_key()
-        if akey == self._akey or sc or any(p.dtype != torch.float32 or not p.is_contiguous() or not p.is_cuda for p in ad):
-            return None
-        T = len(self.tasks)
-        return akey, (self.spec, ad[0].detach(), ad[1].detach(), [p.detach() for p in ad[2:2 + T]],
-                      [p.detach() for p in ad[2 + T:2 + 2 * T]])
-
     def stage(self):
         w = self.linear.weight
         if not w.is_cuda:
@@ -235,24 +223,89 @@ class LinearEngine:
         return dx, grads
 
 
-def stage_many(engines):
-    """Refresh the packed bf16 adapter operands of every engine whose fp32 masters changed (one optimizer step = all of
-    them) in ONE launch instead of one per layer; `LinearEngine.stage` then finds them current."""
-    todo = []
-    for e in engines:
-        j = e.pack_job()
-        if j is not None:
-            todo.append((e, j[0], j[1]))
-    if len(todo) < 2:
-        return 0          # a single stale layer: its own stage() handles it
-    dev = todo[0][2][1].device
-    if any(t[2][1].device != dev for t in todo):
-        return 0
-    with torch.no_grad():
-        packed = ops.pack_adapters_many([t[2] for t in todo])
-    for (e, akey, _), pk in zip(todo, packed):
-        e._packed, e._akey = pk, akey
-    return len(todo)
+class AdapterStager:
+    """Re-packs the bf16 adapter operands of ALL layers of a model in one launch when an optimizer step (or any in-place
+    update that bumps `_version`) changed their fp32 masters; `LinearEngine.stage` then finds them current. Job tables
+    (mtl_pack_job per layer) and operand views are built once, for two alternating buffers: a refresh costs one pass over
+    the parameters' version counters on the host, and the operands a graph was recorded with stay intact until the
+    refresh after next (the fp32 masters of such a graph would be stale for autograd as well).
+    Layers with a trainable LoRA scale (folded into B at staging time) keep staging themselves."""
+
+    def __init__(self, modules):
+        self.modules = list(modules)
+        self._sig = None
+
+    def _build(self, engines):
+        self.items = []
+        for e in engines:
+            if e.spec.r_shared == 0 or e.scales():
+                continue
+            ad = e.adapters()
+            if any((not p.is_cuda) or p.dtype != torch.float32 or not p.is_contiguous() for p in ad):
+                continue
+            self.items.append((e, ad))
+        self.flat = [p for _, ad in self.items for p in ad]
+        self.ptrs = [p.data_ptr() for p in self.flat]
+        self.spans, k = [], 0
+        for _, ad in self.items:
+            self.spans.append((k, k + len(ad)))
+            k += len(ad)
+        self.versions = None
+        self.side = 0
+        self.arrs, self.packed = [], []
+        if len(self.items) < 2 or any(p.device != self.flat[0].device for p in self.flat):
+            self.items = []
+            return
+        offs, n = [], 0
+        for e, _ in self.items:
+            offs.append(n)
+            n += (2 * e.spec.R_pad * (e.spec.K + e.spec.Nf) + 7) // 8 * 8     # keeps every operand 16-byte aligned
+        for _ in range(2):
+            buf = torch.empty(n, dtype=BF16, device=self.flat[0].device)
+            arr = (ops.N.PackJob * len(self.items))()
+            views = []
+            for j, (e, ad) in enumerate(self.items):
+                spec, T = e.spec, len(e.tasks)
+                R, K, Nf, o = spec.R_pad, spec.K, spec.Nf, offs[j]
+                pk = (buf[o:o + R * K].view(R, K), buf[o + R * K:o + R * (K + Nf)].view(Nf, R),
+                      buf[o + R * (K + Nf):o + R * (2 * K + Nf)].view(K, R),
+                      buf[o + R * (2 * K + Nf):o + 2 * R * (K + Nf)].view(R, Nf))
+                jb = arr[j]
+                jb.cfg = spec.cfg(1, False)
+                jb.a_shared, jb.b_shared = ad[0].data_ptr(), ad[1].data_ptr()
+                for t in range(T):
+                    jb.a_tasks[t], jb.b_tasks[t] = ad[2 + t].data_ptr(), ad[2 + T + t].data_ptr()
+                jb.a_cat, jb.b_cat, jb.a_cat_t, jb.b_cat_t = (t.data_ptr() for t in pk)
+                views.append(pk)
+            self.arrs.append(arr)
+            self.packed.append(views)
+
+    def refresh(self):
+        """-> number of layers re-packed (0: everything was current)."""
+        engines = [m.engine for m in self.modules]
+        sig = tuple(map(id, engines))          # MTLoRALinear.merge() swaps the engine in effect
+        if sig != self._sig:
+            self._build(engines)
+            self._sig = sig
+        if not self.items:
+            return 0                           # nothing to do, or a single layer: its own stage() handles it
+        vers = [p._version for p in self.flat]
+        if vers == self.versions and all(e._akey is not None for e, _ in self.items):
+            return 0
+        if [p.data_ptr() for p in self.flat] != self.ptrs:      # parameters moved (.to(), .cuda()): new job tables
+            self._build(engines)
+            if not self.items:
+                return 0
+            vers = [p._version for p in self.flat]
+        self.side ^= 1
+        with torch.cuda.device(self.flat[0].device):
+            ops.N.call("mtl_linear_pack_many", self.arrs[self.side], len(self.items), ops.N.stream())
+        keys = list(zip(self.ptrs, vers))
+        for (e, _), pk, (k0, k1) in zip(self.items, self.packed[self.side], self.spans):
+            e._packed = pk
+            e._akey = tuple(keys[k0:k1])
+        self.versions = vers
+        return len(self.items)
 
 
 class _LinearFn(torch.autograd.Function):

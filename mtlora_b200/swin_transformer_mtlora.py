@@ -19,7 +19,7 @@ import torch.nn as nn
 from torch import Tensor
 
 from . import ops
-from .lora import LinearEngine, MTLoRALinear, _new_seed, run_linear_standalone, stage_many
+from .lora import AdapterStager, LinearEngine, MTLoRALinear, _new_seed, run_linear_standalone
 
 BF16 = torch.bfloat16
 
@@ -1064,11 +1064,11 @@ class SwinTransformerMTLoRA(nn.Module):
 
     def _stage_adapters(self):
         """Re-pack the bf16 adapter operands of all layers in one launch when an optimizer step changed them."""
-        mods = self.__dict__.get("_lin_modules")
-        if mods is None:
-            mods = [m for m in self.modules() if m is not self and hasattr(type(m), "engine")]
-            self.__dict__["_lin_modules"] = mods
-        stage_many([m.engine for m in mods])
+        st = self.__dict__.get("_adapter_stager")
+        if st is None:
+            st = AdapterStager(m for m in self.modules() if m is not self and hasattr(type(m), "engine"))
+            self.__dict__["_adapter_stager"] = st
+        return st.refresh()
 
     def forward_features(self, x, return_stages=False, flatten_ft=False):
         if self.training and torch.is_grad_enabled():

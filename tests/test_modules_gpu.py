@@ -257,10 +257,9 @@ def test_backbone_vs_oracle_tasks(S):
             close(v.grad, p[n].grad, 5e-2, what="d." + n)
 
 
-def test_stage_many_equals_per_layer_staging(S):
-    """SwinTransformerMTLoRA re-packs the adapters of all layers in one launch per optimizer step (lora.stage_many);
+def test_adapter_stager_equals_per_layer_staging(S):
+    """SwinTransformerMTLoRA re-packs the adapters of all layers in one launch per optimizer step (lora.AdapterStager);
     the operands equal what every layer's own LinearEngine.stage() produces, and a parameter update makes them stale."""
-    from mtlora_b200 import lora as L
     tasks = ["normals", "semseg"]
     ranks = [{"shared": 16, "normals": 4, "semseg": 4}] * 4
     net = quiet(S.SwinTransformerMTLoRA, img_size=224, num_classes=0, depths=[2, 2, 2, 2], drop_path_rate=0.0,
@@ -270,14 +269,17 @@ def test_stage_many_equals_per_layer_staging(S):
     mods = [m for m in net.modules() if m is not net and hasattr(type(m), "engine")]
     lora = [m for m in mods if m.engine.spec.r_shared > 0]
     assert len(lora) >= 32
-    assert L.stage_many([m.engine for m in mods]) == len(lora)
+    assert net._stage_adapters() == len(lora)
     many = [tuple(t.clone() for t in m.engine._packed) for m in lora]
-    assert L.stage_many([m.engine for m in mods]) == 0          # nothing stale now
+    assert net._stage_adapters() == 0                            # nothing stale now
     for m in lora:
         m.engine.invalidate()
         m.engine.stage()
     for m, got in zip(lora, many):
         assert all(torch.equal(a, b) for a, b in zip(got, m.engine._packed))
+    assert net._stage_adapters() == 0                            # per-layer staging left everything current
+    lora[3].engine.invalidate()
+    assert net._stage_adapters() == len(lora)                    # an invalidated layer is noticed
     img = detgen.uniform("sm.img", (1, 3, 224, 224), -2.0, 2.0).cuda()
     with torch.autocast("cuda", dtype=torch.bfloat16):
         y0 = net(img, return_stages=True)[3][0].float()
@@ -285,10 +287,17 @@ def test_stage_many_equals_per_layer_staging(S):
         for n, q in net.named_parameters():
             if "lora_" in n:
                 q.mul_(1.5)
-    assert L.stage_many([m.engine for m in mods]) == len(lora)   # an in-place update bumps _version
+    assert net._stage_adapters() == len(lora)                    # an in-place update bumps _version
     with torch.autocast("cuda", dtype=torch.bfloat16):
         y1 = net(img, return_stages=True)[3][0].float()
     assert not torch.equal(y0, y1)
+    # the packed operands of the one-launch path equal a fresh per-layer staging of the updated parameters
+    many = [tuple(t.clone() for t in m.engine._packed) for m in lora]
+    for m in lora:
+        m.engine.invalidate()
+        m.engine.stage()
+    for m, got in zip(lora, many):
+        assert all(torch.equal(a, b) for a, b in zip(got, m.engine._packed))
 
 
 def test_training_mode_stochastic(S):

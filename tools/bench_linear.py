@@ -27,6 +27,9 @@ CASES = {
     "s1_fc2_bwd": (100352, 768, 192, 64, [4] * 4, "fc2_bwd"),
     "s1_fc1_fwd": (100352, 192, 768, 64, [4] * 4, "fc1"),
     "s0_fc2_bwd": (401408, 384, 96, 64, [], "fc2_bwd_single"),
+    "s0_fc1_fwd": (401408, 96, 384, 64, [], "fc1_single"),
+    "s0_fc2_fwd": (401408, 384, 96, 64, [], "fc2_single"),
+    "s0_fc1_bwd": (401408, 96, 384, 64, [], "fc1_bwd_single"),
     "s0_proj_bwd": (401408, 96, 96, 64, [], "proj_bwd_single"),
     "s2_qkv_fwd": (25088, 384, 1152, 64, [], "qkv"),
     "s2_fc2_fwd": (25088, 1536, 384, 64, [], "fc2_single"),
