@@ -29,11 +29,13 @@ namespace {
 
 constexpr int XG_ROWS = 64;                 // contraction rows per pipeline stage
 constexpr int XG_BOX_BYTES = XG_ROWS * 128; // one [64 x 64] bf16 box
-constexpr int XG_STAGE_BYTES = 3 * XG_BOX_BYTES;   // wide box 0, wide box 1, rank box
-constexpr int XG_STAGES = 8;
+constexpr int XG_STAGE_BYTES = 3 * XG_BOX_BYTES;   // wide box 0, wide box 1, rank box (rank_boxes == 1)
+constexpr int XG_STAGES = 8;                // ring depth with one rank box per stage; fewer when the stages are wider
+constexpr int XG_RING_BYTES = XG_STAGES * XG_STAGE_BYTES;
+constexpr int XG_MAX_RANK_BOXES = 4;        // UMMA N = 64 .. 256
 constexpr int XG_MAX_GROUPS = 24;
 constexpr int XG_THREADS = 384;             // 4 control warps, 4 epilogue warps, 4 row-scale warps
-constexpr int XG_TMEM_COLS = 128;           // 2 accumulators x 64 columns
+constexpr int XG_TMEM_COLS = 512;           // 2 accumulators x (64 * rank_boxes <= 256) columns
 
 struct XGroup {
   int wide_map, wide_stream, width, n_wt;   // wide operand: tensor map 0/1, stream (3rd coordinate), columns, 128-col tiles
@@ -50,7 +52,11 @@ struct XParams {
   long M;
   long m_chunk;            // rows per unit (multiple of XG_ROWS)
   int n_groups, n_jobs, n_splits, n_units;
-  int rows_per_sample, n_samples, any_rowscale, pad_;
+  int rows_per_sample, n_samples, any_rowscale;
+  // 64-column boxes of the rank operand per pipeline stage = per accumulator (1..4). A wide "rank" operand (mtl_xty on
+  // a trainable dense weight: dW = dY^T X, 192..768 columns on both sides) then re-streams the other operand once per
+  // 256 columns instead of once per 64 (the kernel is bound by operand traffic from L2)
+  int rank_boxes;
   XGroup g[XG_MAX_GROUPS];
 };
 
@@ -78,9 +84,10 @@ __device__ __forceinline__ Unit decode_unit(const XParams& p, int u) {
   if (lim < 0) lim = 0;
   t.wide_c0 = c0 < lim ? c0 : lim;
   t.lane_lo = c0 - t.wide_c0;
-  t.rank_c0 = g.r0 + rc * 64;
+  const int rcols = 64 * p.rank_boxes;
+  t.rank_c0 = g.r0 + rc * rcols;
   int rv = g.r0 + g.rlen - t.rank_c0;
-  t.rank_valid = rv < 64 ? rv : 64;
+  t.rank_valid = rv < rcols ? rv : rcols;
   t.m_begin = static_cast<long>(s) * p.m_chunk;
   long m_end = t.m_begin + p.m_chunk;
   if (m_end > p.M) m_end = p.M;
@@ -115,7 +122,9 @@ xty_umma_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + XG_STAGES * XG_STAGE_BYTES;
+  const uint32_t bar_base = smem_base + XG_RING_BYTES;
+  const uint32_t stage_bytes = (2 + p.rank_boxes) * XG_BOX_BYTES;
+  const int n_stages = XG_RING_BYTES / stage_bytes;   // 8, 6, 4, 4
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (XG_STAGES + s); };
   auto scaled_bar = [&](int s) { return bar_base + 8u * (2 * XG_STAGES + s); };
@@ -123,7 +132,7 @@ xty_umma_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant
   auto acc_empty = [&](int b) { return bar_base + 8u * (3 * XG_STAGES + 2 + b); };
   const uint32_t tmem_slot = bar_base + 8u * (3 * XG_STAGES + 4);
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + XG_STAGES * XG_STAGE_BYTES + 8u * (3 * XG_STAGES + 4));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + XG_RING_BYTES + 8u * (3 * XG_STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -165,13 +174,16 @@ xty_umma_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant
         const CUtensorMap* rm = g.rank_map ? &tm_r1 : &tm_r0;
         for (int st = 0; st < t.n_steps; ++st) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t dst = smem_base + stage * XG_STAGE_BYTES;
+          const uint32_t dst = smem_base + stage * stage_bytes;
           const int row = static_cast<int>(t.m_begin) + st * XG_ROWS;
-          mbar_arrive_expect_tx(full_bar(stage), XG_STAGE_BYTES);
+          mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
           tma_load_3d(dst, wm, full_bar(stage), t.wide_c0, row, g.wide_stream);
           tma_load_3d(dst + XG_BOX_BYTES, wm, full_bar(stage), t.wide_c0 + 64, row, g.wide_stream);
-          tma_load_2d(dst + 2 * XG_BOX_BYTES, rm, full_bar(stage), t.rank_c0, row);
-          if (++stage == XG_STAGES) {
+          // (boxes past the last column of the operand are zero-filled by TMA; columns past the group's range are
+          // computed and dropped by the epilogue)
+          for (int b = 0; b < p.rank_boxes; ++b)
+            tma_load_2d(dst + (2 + b) * XG_BOX_BYTES, rm, full_bar(stage), t.rank_c0 + 64 * b, row);
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -182,8 +194,9 @@ xty_umma_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant
   } else if (warp == 1) {
     // ============================================= MMA issuer =============================================
     if (lane == 0) {
-      // M = 128 (wide columns), N = 64 (rank columns), both operands MN-major
-      const uint32_t idesc = umma_idesc_bf16_m128(64) | (1u << 15) | (1u << 16);
+      // M = 128 (wide columns), N = 64 * rank_boxes (rank columns), both operands MN-major
+      const uint32_t idesc = umma_idesc_bf16_m128(64 * p.rank_boxes) | (1u << 15) | (1u << 16);
+      const uint32_t acc_cols = 64 * p.rank_boxes;
       int stage = 0;
       uint32_t phase = 0, ub = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++ub) {
@@ -191,11 +204,11 @@ xty_umma_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant
         const uint32_t buf = ub & 1u;
         mbar_wait(acc_empty(buf), ((ub >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * 64;
+        const uint32_t d_tmem = tmem_base + buf * acc_cols;
         for (int st = 0; st < t.n_steps; ++st) {
           mbar_wait(p.any_rowscale ? scaled_bar(stage) : full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t base = smem_base + stage * XG_STAGE_BYTES;
+          const uint32_t base = smem_base + stage * stage_bytes;
 #pragma unroll
           for (int ks = 0; ks < XG_ROWS / 16; ++ks) {
             const uint64_t adesc = umma_desc_mn_sw128(base + ks * 2048, XG_BOX_BYTES);
@@ -203,7 +216,7 @@ xty_umma_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant
             umma_bf16(d_tmem, adesc, bdesc, idesc, (st | ks) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));
-          if (++stage == XG_STAGES) {
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -227,10 +240,10 @@ xty_umma_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant
       const int w = t.wide_c0 + li;
       const bool ok = li >= t.lane_lo && w < g.width;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 4 * p.rank_boxes; ++c) {
         if (c * 16 >= t.rank_valid) break;
         uint32_t r[16];
-        tmem_ld16(t_lane + buf * 64 + c * 16, r);
+        tmem_ld16(t_lane + buf * 64 * p.rank_boxes + c * 16, r);
         tmem_ld_wait();
         if (ok) {
           if (g.kind == 0) {
@@ -276,7 +289,7 @@ xty_umma_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant
           if (smp >= p.n_samples) smp = p.n_samples - 1;
           const float s = rs[smp];
           if (s != 1.f) {
-            uint8_t* rowp = smem_gen + stage * XG_STAGE_BYTES + 2 * XG_BOX_BYTES + row * 128 + half * 64;
+            uint8_t* rowp = smem_gen + stage * stage_bytes + 2 * XG_BOX_BYTES + row * 128 + half * 64;   // rank_boxes == 1
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               uint4 v = *reinterpret_cast<uint4*>(rowp + 16 * i);
@@ -289,7 +302,7 @@ xty_umma_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant
           fence_proxy_async_smem();
         }
         mbar_arrive(scaled_bar(stage));
-        if (++stage == XG_STAGES) {
+        if (++stage == n_stages) {
           stage = 0;
           phase ^= 1u;
         }
@@ -320,6 +333,21 @@ int launch_xty_groups(const XtyOperand* wide, const XtyOperand* rank, const XtyJ
   p.n_groups = n_groups;
   p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : 1;
   p.n_samples = static_cast<int>((M + p.rows_per_sample - 1) / p.rows_per_sample);
+  // rank boxes per stage: as many as the widest rank range needs (DropPath row scaling rewrites ONE box per stage)
+  p.rank_boxes = 1;
+  {
+    int widest = 0;
+    bool scaled = false;
+    for (int i = 0; i < n_groups; ++i) {
+      if (groups[i].rlen > widest) widest = groups[i].rlen;
+      if (groups[i].rowscale != nullptr) scaled = true;
+    }
+    if (!scaled) {
+      p.rank_boxes = (widest + 63) / 64;
+      if (p.rank_boxes > XG_MAX_RANK_BOXES) p.rank_boxes = XG_MAX_RANK_BOXES;
+      if (p.rank_boxes < 1) p.rank_boxes = 1;
+    }
+  }
   int jobs = 0;
   for (int i = 0; i < n_groups; ++i) {
     const XtyJobGroup& s = groups[i];
@@ -339,7 +367,7 @@ int launch_xty_groups(const XtyOperand* wide, const XtyOperand* rank, const XtyJ
     g.rank_map = s.rank_op;
     g.r0 = s.r0;
     g.rlen = s.rlen;
-    g.n_rc = (s.rlen + 63) / 64;
+    g.n_rc = (s.rlen + 64 * p.rank_boxes - 1) / (64 * p.rank_boxes);
     g.kind = s.out_rank_major ? 1 : 0;
     g.out_ld = s.out_ld;
     g.out = s.out;

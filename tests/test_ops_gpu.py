@@ -478,7 +478,8 @@ def test_xty(ops):
 
 
 # alpha == 1 takes the tcgen05 reduction (xty_sm100.cu): MN-major operands, 128-column tiles of the wider matrix
-# (shifted last tile when the width is not a multiple of 128), 64-column chunks of the narrower one, row splits.
+# (shifted last tile when the width is not a multiple of 128), chunks of up to 256 columns (1-4 boxes of 64) of the
+# narrower one, row splits.
 @pytest.mark.parametrize("M,a,b", [
     (5000, 192, 384),     # dW of PatchMerging.reduction at stage 0 (wide = Q)
     (777, 96, 200),       # ragged rows, wide tile shifted left (200 = 128 + 72)
@@ -486,6 +487,10 @@ def test_xty(ops):
     (20000, 24, 96),      # narrow rank operand (24 columns), single partially filled wide tile
     (64, 128, 128),       # a single pipeline step
     (130000, 80, 328),    # many row splits; rank range crossing a 64-column chunk boundary
+    (25088, 384, 768),    # stage-1 reduction: 256-column accumulators, second chunk half empty (384 = 256 + 128)
+    (6272, 768, 1536),    # stage-2 reduction: three 256-column chunks
+    (3000, 200, 456),     # ragged on both sides with four rank boxes (200 = 3 * 64 + 8)
+    (900, 136, 136),      # three rank boxes, the last one holding 8 columns
 ])
 def test_xty_tensor_core_path(ops, M, a, b):
     P = bf(dev(detgen.uniform(f"xty2.p.{M}.{a}", (M, a))))
