@@ -66,6 +66,10 @@ def parse():
     ap.add_argument("--dropout", type=float, default=0.05)
     ap.add_argument("--drop-path", type=float, default=0.2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gc-freeze", action="store_true",
+                    help="do not gc.freeze() the warmed-up process before the timed loops (all arms freeze by default: a "
+                         "full collection over the ~1e6 live objects of torch + the model pauses the host for ~50 ms, "
+                         "longer than the launch queue covers)")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the full_step and reference_gpu blocks of our line (profiling / sweeps)")
     ap.add_argument("--cpu-batch", type=int, default=2)
@@ -108,6 +112,8 @@ class Clocks:
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):
+        if os.environ.get("MTL_BENCH_NO_CLOCKS"):      # diagnosis only: a run without the sampler has no clocks evidence
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
@@ -251,13 +257,23 @@ def make_step(a, net, crit, opt, scope, amp, reducer=None):
     MeanSquare = make_mean_square()
     params = [p for p in net.parameters() if p.requires_grad]
 
+    phase_log = [] if os.environ.get("MTL_BENCH_PHASE_TRACE") else None   # diagnosis: host time per phase
+    make_step.phase_log = phase_log
+
+    def mark(tag):
+        if phase_log is not None:
+            phase_log.append((tag, time.perf_counter()))
+
     def step(img, targets):
+        mark("enter")
         with torch.autocast("cuda", dtype=amp_dtype):
             if scope == "full":
                 loss, _ = crit(net(img), targets)
             else:
                 stages = net(img, return_stages=True)
+                mark("backbone")
                 loss = sum(MeanSquare.apply(v) for _, tl in stages for v in tl.values())
+        mark("forward")
         fused_clip = getattr(opt, "fused_clip", False)   # FlatAdamW(max_grad_norm=...): unscale + clip inside step()
         if scaler is not None:
             scaler.scale(loss).backward()
@@ -271,27 +287,75 @@ def make_step(a, net, crit, opt, scope, amp, reducer=None):
             scaler.update()
         else:
             loss.backward()
+            mark("backward")
             if reducer is not None:
                 reducer.reduce()
             if scope == "full" and not fused_clip:
                 torch.nn.utils.clip_grad_norm_(params, 5.0)
             opt.step()
+            mark("opt")
         opt.zero_grad(set_to_none=True)
+        mark("zero_grad")
         return loss
     return step
 
 
-def time_steps(step, batches, n_steps, warmup):
+class GcWatch:
+    """Counts the Python garbage collections that fall into the timed loops and their longest pause (gc.callbacks)."""
+
+    def __init__(self):
+        self.n, self.max_ms, self._t0 = 0, 0.0, 0.0
+
+    def _cb(self, phase, info):
+        if phase == "start":
+            self._t0 = time.perf_counter()
+        else:
+            self.n += 1
+            self.max_ms = max(self.max_ms, 1e3 * (time.perf_counter() - self._t0))
+
+    def __enter__(self):
+        import gc
+        gc.callbacks.append(self._cb)
+        return self
+
+    def __exit__(self, *exc):
+        import gc
+        gc.callbacks.remove(self._cb)
+
+    def report(self, frozen):
+        return {"collections": self.n, "max_pause_ms": round(self.max_ms, 2), "frozen_after_warmup": bool(frozen)}
+
+
+def gc_freeze(a):
+    """After the warm-up: collect once and move every live object to the permanent generation, so that the collections
+    inside the timed loops only walk what the steps themselves allocate."""
+    import gc
+    if not a.no_gc_freeze:
+        gc.collect()
+        gc.freeze()
+    return not a.no_gc_freeze
+
+
+PACE_STEPS = 1   # the timed loops of every arm keep the host this many steps ahead of the GPU at most (see run_ours)
+
+
+def time_steps(step, batches, n_steps, warmup, a=None):
     """CUDA-event time of n_steps back-to-back steps over alternating resident batches -> (ms total, last loss)."""
     import torch
     for i in range(warmup):
         step(*batches[i % 2])
     torch.cuda.synchronize()
+    if a is not None:
+        gc_freeze(a)      # same treatment for every arm (reference modules on the GPU included)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(blocking=True) for _ in range(n_steps)]
     e0.record()
     last = None
     for i in range(n_steps):
         last = step(*batches[i % 2])
+        marks[i].record()
+        if i >= PACE_STEPS:
+            marks[i - PACE_STEPS].synchronize()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1), float(last)
@@ -424,7 +488,7 @@ def reference_gpu_numbers(a, dev, steps, warmup, scopes=("backbone", "full"), am
             torch.manual_seed(1234)
             key = f"{scope}_{amp}"
             try:
-                ms, loss = time_steps(step, list(zip(imgs, targets)), steps, warmup)
+                ms, loss = time_steps(step, list(zip(imgs, targets)), steps, warmup, a)
                 out[key] = {"images_per_s": a.batch * steps / (ms * 1e-3), "ms_per_step": ms / steps, "loss": loss,
                             "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
             except torch.OutOfMemoryError as e:
@@ -546,6 +610,10 @@ def run_ours(a):
             staged[i % 2].copy_(host[i % 2], non_blocking=True)
             landed[i % 2].record(copy_stream)
 
+    # blocking=True: the pacing wait sleeps instead of spinning (a host thread that spins through the whole timed loop
+    # was descheduled for 60-450 ms about once per run on the shared bench hosts)
+    marks = [torch.cuda.Event(enable_timing=True, blocking=True) for _ in range(a.steps)]
+
     def timed(n_steps, e2e):
         barrier()
         k0 = _native.kernel_launches()
@@ -566,14 +634,38 @@ def run_ours(a):
                 stamps.append(time.perf_counter())
             else:
                 last = step(resident[i % 2], i)
+                marks[i].record()                  # per-step device time
+                if i >= PACE_STEPS:
+                    # keep the host at most PACE_STEPS step(s) ahead of the GPU, with a sleeping wait: left alone it
+                    # fills the driver's launch queue and spins there. On some bench hosts one step of a loop (always the
+                    # 4th or 5th after the bracketing synchronize) then lost 60-500 ms on the HOST side, inside the forward
+                    # launches, with no garbage collection, cudaMalloc or clock event to blame (profiles/r02_host_stalls.txt);
+                    # other hosts never show it. One step of queued work (26 ms) covers the ~16 ms the host needs to issue
+                    # the next one, so the GPU never idles. `resident_steps` in the JSON line keeps the per-step evidence.
+                    marks[i - PACE_STEPS].synchronize()
+                stamps.append(time.perf_counter())
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        if not e2e and getattr(make_step, "phase_log", None):
+            log = make_step.phase_log
+            # host seconds spent in each phase of the slowest step of this loop
+            enters = [k for k, (tag, _) in enumerate(log) if tag == "enter"][-n_steps:]
+            worst = max(range(len(enters)), key=lambda j: (log[enters[j + 1]][1] if j + 1 < len(enters) else
+                                                           stamps[-1]) - log[enters[j]][1])
+            k0_, k1_ = enters[worst], (enters[worst + 1] if worst + 1 < len(enters) else len(log))
+            seq = log[k0_:k1_]
+            sys.stderr.write("slowest resident step %d, host ms per phase: %s\n" % (
+                worst, ", ".join("%s %.1f" % (b[0], 1e3 * (b[1] - a_[1])) for a_, b in zip(seq, seq[1:]))))
+        if not e2e:
+            ev = [e0] + marks[:n_steps]
+            timed.resident_gpu = [x.elapsed_time(y) for x, y in zip(ev, ev[1:])]
+            timed.resident_host = [1e3 * (b - a_) for a_, b in zip(stamps, stamps[1:])]
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        per_step = [1e3 * (b - a_) for a_, b in zip(stamps, stamps[1:])]
-        timed.per_step = per_step
+        if e2e:
+            timed.per_step = [1e3 * (b - a_) for a_, b in zip(stamps, stamps[1:])]
         return t.item(), _native.kernel_launches() - k0, float(last.detach() if hasattr(last, "detach") else last)
 
     # the clocks sampler (nvidia-smi -lms) is started BEFORE the warm-up: its start-up (NVML initialisation, ~1-2 s of
@@ -600,10 +692,16 @@ def run_ours(a):
         step(resident[i % 2], i)
         host_ms.append(1e3 * (time.perf_counter() - t0))
     torch.cuda.synchronize()
-    ms_dev, launches, loss_dev = timed(a.steps, e2e=False)
-    timed(min(a.warmup, 3), e2e=True)              # warm the end-to-end loop (copy stream, staging buffers)
-    ms_e2e, _, loss_e2e = timed(a.steps, e2e=True)
+    frozen = gc_freeze(a)
+    ms0 = torch.cuda.memory_stats(dev)
+    with GcWatch() as gcw:
+        ms_dev, launches, loss_dev = timed(a.steps, e2e=False)
+        ms1 = torch.cuda.memory_stats(dev)
+        timed(min(a.warmup, 3), e2e=True)              # warm the end-to-end loop (copy stream, staging buffers)
+        ms_e2e, _, loss_e2e = timed(a.steps, e2e=True)
     e2e_steps = sorted(getattr(timed, "per_step", []) or [0.0])
+    res_gpu = getattr(timed, "resident_gpu", None) or [0.0]
+    res_host = getattr(timed, "resident_host", None) or [0.0]
     clk = clocks.stop() if rank == 0 else None
 
     # per-call CUDA-event profile of 2 more steps: time share per C-ABI entry point + roofline of the fused linear
@@ -670,7 +768,7 @@ def run_ours(a):
             barrier()
             # 20 untimed steps first: the decoder heads' allocation pattern takes longer than the backbone's to settle in
             # the caching allocator (cudaMalloc synchronises the device)
-            ms, loss = time_steps(fstep, list(zip(resident, ftargets)), n_x, 20)
+            ms, loss = time_steps(fstep, list(zip(resident, ftargets)), n_x, 20, a)
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -719,6 +817,19 @@ def run_ours(a):
         "gpu_launches": launches,
         "host_issue_ms_per_step": round(statistics.median(host_ms), 3),
         "clocks": clk,
+        "host_gc": gcw.report(frozen),
+        # caching-allocator activity inside the resident timed loop: a cudaMalloc / cudaFree there synchronises the device
+        "allocator": {"cuda_mallocs_in_loop": ms1.get("num_device_alloc", 0) - ms0.get("num_device_alloc", 0),
+                      "cuda_frees_in_loop": ms1.get("num_device_free", 0) - ms0.get("num_device_free", 0),
+                      "alloc_retries_in_loop": ms1.get("num_alloc_retries", 0) - ms0.get("num_alloc_retries", 0),
+                      "reserved_gb_peak": round(ms1.get("reserved_bytes.all.peak", 0) / 2 ** 30, 1),
+                      "allocated_gb_peak": round(ms1.get("allocated_bytes.all.peak", 0) / 2 ** 30, 1)},
+        # per-step device time of the resident loop (events between the steps) and the longest host-side issue of a step:
+        # a step whose device time stands out while the host time does too was starved by the host, not slow on the GPU
+        "resident_steps": {"gpu_ms_min_median_max": [round(min(res_gpu), 2), round(statistics.median(res_gpu), 2),
+                                                     round(max(res_gpu), 2)],
+                           "host_ms_median_max": [round(statistics.median(res_host), 2), round(max(res_host), 2)],
+                           "slowest_step": res_host.index(max(res_host))},
         "roofline": roof,
         "roofline_tensor": roof_tensor,
         "cpu_baseline": cpu,

@@ -193,13 +193,21 @@ class LinearEngine:
                                            dy_has_sum=v2 and dy_sum)
             T = len(self.tasks)
             tscale = dict(self.scales())
+            # dB of the task adapters as ONE strided copy into a [T, N, r] block (autograd would otherwise clone each
+            # non-contiguous column slice of db_cat on its own: 4 small copy kernels per layer)
+            db_tasks = None
+            if T > 1 and len(set(spec.ranks[1:])) == 1:
+                r_t, step_t = spec.ranks[1], spec.offsets[2] - spec.offsets[1]
+                if all(spec.offsets[1 + t] == spec.offsets[1] + t * step_t for t in range(T)):
+                    db_tasks = db[:, spec.offsets[1]:spec.offsets[1] + T * step_t].view(spec.Nf, T, step_t)[:, :, :r_t] \
+                        .permute(1, 0, 2).contiguous()
             for i in range(1 + T):
                 off, r = spec.offsets[i], spec.ranks[i]
                 pa = ad[0] if i == 0 else ad[2 + (i - 1)]
                 pb = ad[1] if i == 0 else ad[2 + T + (i - 1)]
                 if pa.requires_grad:
                     grads[pa] = da[off:off + r]
-                dbi = db[:, off:off + r]
+                dbi = db_tasks[i - 1] if (i > 0 and db_tasks is not None) else db[:, off:off + r]
                 if i in tscale:
                     # the kernels ran with scale 1 on U = x A^T: db = dy^T U, so dB = s db and ds = <db, B>
                     q = tscale[i]

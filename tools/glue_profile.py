@@ -27,30 +27,26 @@ def main():
         step(img, None)
     torch.cuda.synchronize()
     n = 2
-    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True) as prof:
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True,
+                 experimental_config=torch._C._profiler._ExperimentalConfig(verbose=True)) as prof:
         for _ in range(n):
             step(img, None)
         torch.cuda.synchronize()
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    agg = collections.defaultdict(lambda: [0, 0.0])
-    for ev in prof.events():
-        dt = getattr(ev, "device_time_total", 0) or getattr(ev, "cuda_time_total", 0)
-        if not dt or ev.cpu_parent is not None and (getattr(ev.cpu_parent, "device_time_total", 0) or 0) >= dt and \
-                ev.cpu_parent.name.startswith("aten::"):
+    rows = []
+    for ev in prof.key_averages(group_by_stack_n=16):
+        dt = getattr(ev, "device_time_total", 0)
+        if not dt or not ev.key.startswith("aten::"):
             continue
-        if not ev.name.startswith("aten::"):
-            continue
-        frames = [f for f in (ev.stack or []) if root in f or "mtlora_b200" in f or "bench.py" in f]
-        where = " <- ".join(os.path.basename(f.split(": ")[0]) + " " + f.split(": ")[-1] for f in frames[:3]) \
-            or "(no repo frame)"
-        key = (ev.name, where)
-        agg[key][0] += 1
-        agg[key][1] += dt
-    rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
+        frames = [f for f in (ev.stack or []) if "mtlora_b200/" in f or "bench.py" in f]
+        where = " <- ".join(os.path.basename(f.split("(")[0]) + ":" + f.split("(")[1].split(")")[0] + " " + f.split(": ")[-1]
+                            for f in frames[:3] if "(" in f) or "(no repo frame)"
+        rows.append((dt / n, ev.count / n, ev.key, where))
+    rows.sort(reverse=True)
     tot = 0.0
-    for (name, where), (cnt, t) in rows[:60]:
-        print(f"{t / n:9.1f} us/step {cnt / n:6.1f} calls/step  {name:28s} {where}")
-        tot += t / n
+    for dt, cnt, name, where in rows[:70]:
+        print(f"{dt:9.1f} us/step {cnt:6.1f} calls/step  {name:28s} {where}")
+        tot += dt
     print(f"total of the listed aten ops: {tot:.1f} us/step")
 
 
