@@ -336,9 +336,6 @@ def gc_freeze(a):
     return not a.no_gc_freeze
 
 
-PACE_STEPS = 1   # the timed loops of every arm keep the host this many steps ahead of the GPU at most (see run_ours)
-
-
 def time_steps(step, batches, n_steps, warmup, a=None):
     """CUDA-event time of n_steps back-to-back steps over alternating resident batches -> (ms total, last loss)."""
     import torch
@@ -348,14 +345,10 @@ def time_steps(step, batches, n_steps, warmup, a=None):
     if a is not None:
         gc_freeze(a)      # same treatment for every arm (reference modules on the GPU included)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    marks = [torch.cuda.Event(blocking=True) for _ in range(n_steps)]
     e0.record()
     last = None
     for i in range(n_steps):
-        last = step(*batches[i % 2])
-        marks[i].record()
-        if i >= PACE_STEPS:
-            marks[i - PACE_STEPS].synchronize()
+        last = step(*batches[i % 2]).item()      # main.py:359-361: the loss is read back every step (see run_ours)
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1), float(last)
@@ -610,9 +603,7 @@ def run_ours(a):
             staged[i % 2].copy_(host[i % 2], non_blocking=True)
             landed[i % 2].record(copy_stream)
 
-    # blocking=True: the pacing wait sleeps instead of spinning (a host thread that spins through the whole timed loop
-    # was descheduled for 60-450 ms about once per run on the shared bench hosts)
-    marks = [torch.cuda.Event(enable_timing=True, blocking=True) for _ in range(a.steps)]
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
 
     def timed(n_steps, e2e):
         barrier()
@@ -635,14 +626,12 @@ def run_ours(a):
             else:
                 last = step(resident[i % 2], i)
                 marks[i].record()                  # per-step device time
-                if i >= PACE_STEPS:
-                    # keep the host at most PACE_STEPS step(s) ahead of the GPU, with a sleeping wait: left alone it
-                    # fills the driver's launch queue and spins there. On some bench hosts one step of a loop (always the
-                    # 4th or 5th after the bracketing synchronize) then lost 60-500 ms on the HOST side, inside the forward
-                    # launches, with no garbage collection, cudaMalloc or clock event to blame (profiles/r02_host_stalls.txt);
-                    # other hosts never show it. One step of queued work (26 ms) covers the ~16 ms the host needs to issue
-                    # the next one, so the GPU never idles. `resident_steps` in the JSON line keeps the per-step evidence.
-                    marks[i - PACE_STEPS].synchronize()
+                # the reference's loop reads the loss back every step (main.py:359-361 `loss_meter.update(loss.item())`);
+                # so does this one. It also keeps the host from running steps ahead of the GPU: left alone it fills the
+                # driver's launch queue, and on some bench hosts one step of such a loop (always the 4th or 5th after the
+                # bracketing synchronize) then lost 60-500 ms on the HOST side with no garbage collection, cudaMalloc or
+                # clock event to blame (profiles/r02_host_stalls.txt) — a loop that waits for each step's result never did.
+                last = last.item()
                 stamps.append(time.perf_counter())
         e1.record()
         barrier()
