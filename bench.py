@@ -604,6 +604,7 @@ def run_ours(a):
             landed[i % 2].record(copy_stream)
 
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
+    free_run = bool(os.environ.get("MTL_BENCH_FREE_RUN"))   # diagnosis: let the host run ahead in the resident loop
 
     def timed(n_steps, e2e):
         barrier()
@@ -631,7 +632,8 @@ def run_ours(a):
                 # driver's launch queue, and on some bench hosts one step of such a loop (always the 4th or 5th after the
                 # bracketing synchronize) then lost 60-500 ms on the HOST side with no garbage collection, cudaMalloc or
                 # clock event to blame (profiles/r02_host_stalls.txt) — a loop that waits for each step's result never did.
-                last = last.item()
+                if not free_run:
+                    last = last.item()
                 stamps.append(time.perf_counter())
         e1.record()
         barrier()
