@@ -252,6 +252,55 @@ def _gradsync_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _attach_worker(rank, world, port, out):
+    """SwinTransformerMTLoRA._attach_grad_sync (called at every training forward): covers every trainable parameter once,
+    is a no-op afterwards, and re-scans when the set of trainable parameters grows (cached parameter list)."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import contextlib
+    import io
+    import types
+    from mtlora_b200 import dist as D
+    from mtlora_b200 import swin_transformer_mtlora as S
+    from mtlora_b200.lora import mark_only_lora_as_trainable
+    tasks = ["normals", "semseg"]
+    ranks = [{"shared": 8, "normals": 4, "semseg": 4}] * 4
+    ns = types.SimpleNamespace(ENABLED=True, R_PER_TASK_LIST=ranks, SHARED_SCALE=[4.0] * 4,
+                               SCALE_PER_TASK_LIST=[{t: 4.0 for t in tasks}] * 4, DROPOUT=[0.0] * 4,
+                               TRAINABLE_SCALE_SHARED=False, TRAINABLE_SCALE_PER_TASK=False, SHARED_MODE="matrix",
+                               INTERMEDIATE_SPECIALIZATION=False, DOWNSAMPLER_ENABLED=False, QKV_ENABLED=True,
+                               PROJ_ENABLED=True, FC1_ENABLED=True, FC2_ENABLED=True, FREEZE_PRETRAINED=True,
+                               R=ranks, R_PER_TASK={t: 4 for t in tasks}, SCALE_PER_TASK={t: 4.0 for t in tasks})
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = S.SwinTransformerMTLoRA(img_size=224, num_classes=0, depths=[2, 2, 2, 2], tasks=tasks, mtlora=ns)
+        mark_only_lora_as_trainable(net, bias="none", freeze_patch_embed=True, freeze_norm=True,
+                                    free_relative_bias=False, freeze_downsample_reduction=True)
+    covered = lambda: sum(getattr(p, D._SYNC_ATTR, None) is not None for p in net.parameters())
+    n_train = sum(p.requires_grad for p in net.parameters())
+    ok = 0 < n_train < sum(1 for _ in net.parameters()) and covered() == 0
+    net._attach_grad_sync()
+    ok = ok and covered() == n_train and len(net.__dict__["_grad_syncs"]) == 1
+    net._attach_grad_sync()                         # nothing changed: no second reducer, no re-scan
+    ok = ok and len(net.__dict__["_grad_syncs"]) == 1
+    for p in net.patch_embed.parameters():          # unfreeze more parameters after the first "forward"
+        p.requires_grad_(True)
+    net._attach_grad_sync()
+    n2 = sum(p.requires_grad for p in net.parameters())
+    ok = ok and n2 > n_train and covered() == n2 and len(net.__dict__["_grad_syncs"]) == 2
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_backbone_attaches_grad_sync_once_and_rescans_gloo_world2():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_attach_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}
+
+
 def test_grad_sync_hooks_gloo_world2():
     world = 2
     mgr = mp.Manager()
