@@ -1084,11 +1084,14 @@ class SwinTransformerMTLoRA(nn.Module):
     def forward_features(self, x, return_stages=False, flatten_ft=False):
         if self.training and torch.is_grad_enabled():
             self._attach_grad_sync()
-        if x.is_cuda:
-            # (launching this on a side stream under the patch embedding was measured 0.2 ms per step SLOWER: the two
-            # kernels slow each other down by more than the 90 us of packing they hide, gpurun_out/overlap_ab.txt)
-            self._stage_adapters()
+        staging_due = x.is_cuda
         x = self.patch_embed(x)
+        if staging_due:
+            # after the patch embedding has been launched: a loop that reads its loss back every step starts each step
+            # with an idle GPU, so the first launch should leave the host as early as possible (the patch embedding needs
+            # no adapters). (Launching the packing on a side stream UNDER the patch embedding was measured 0.2 ms per step
+            # slower: the two kernels slow each other down by more than the 90 us they hide.)
+            self._stage_adapters()
         if self.ape:
             x = x + self.absolute_pos_embed
         x = self.pos_drop(x)
